@@ -1,0 +1,244 @@
+// brb_cabi.cu — the extern "C" boundary declared in include/brb.h: plain pointers and sizes, no torch
+// types.  Owns device allocations for the SoA env state, launches the kernels in brb_kernels.cu.
+// There is no CPU path: without a CUDA device every entry point returns BRB_ECUDA.
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "../../include/brb.h"
+#include "brb_internal.h"
+
+extern "C" {
+void brb_launch_step(int kind, const BrbModelConsts *c, const BrbState *S, const float *actions, float *obs, float *reward,
+                     uint8_t *done, uint8_t *truncated, float *terminal_obs, float *ep_return, int32_t *ep_len,
+                     const double *replay_u, cudaStream_t stream);
+void brb_launch_reset(int kind, const BrbState *S, float *obs, const double *replay_u, cudaStream_t stream);
+void brb_launch_get_state(const BrbState *S, double *qpos, double *qvel, double *xquat, cudaStream_t stream);
+void brb_launch_set_state(const BrbState *S, const double *qpos, const double *qvel, cudaStream_t stream);
+void brb_launch_get_elapsed(const BrbState *S, int32_t *out, cudaStream_t stream);
+void brb_launch_ffma_probe(float *out, int blocks, int threads, int iters, cudaStream_t stream);
+}
+
+struct BrbModel {
+  BrbModelConsts consts;
+  double *time_table;   // device
+  int n_time;
+  int device;
+};
+
+struct BrbEnv {
+  const BrbModel *model;
+  BrbState S;
+  void *arena;          // one allocation backing every SoA column
+  int64_t launches;
+  // device staging for brb_env_step_host
+  float *d_actions, *d_obs, *d_reward, *d_tobs, *d_epret;
+  uint8_t *d_done, *d_trunc;
+  int32_t *d_eplen;
+  cudaStream_t host_stream;
+};
+
+#define CK(x) do { if ((x) != cudaSuccess) { cudaGetLastError(); return BRB_ECUDA; } } while (0)
+
+extern "C" int brb_version(void) { return 100; }
+
+extern "C" const char *brb_strerror(int code) {
+  switch (code) {
+    case BRB_OK: return "ok";
+    case BRB_EINVAL: return "invalid argument";
+    case BRB_ENOMEM: return "out of memory";
+    case BRB_ECUDA: return "CUDA error (no device, launch failure or bad device pointer)";
+    default: return "unknown error";
+  }
+}
+
+extern "C" int brb_model_create(const BrbModelConsts *consts, const double *time_table_host, int n_time, int device, BrbModel **out) {
+  if (!consts || !time_table_host || !out || n_time < consts->max_episode_steps + 2) return BRB_EINVAL;
+  if (consts->env_kind < BRB_ENV01_V1 || consts->env_kind > BRB_ENV01_V3 || consts->frame_skip < 1) return BRB_EINVAL;
+  CK(cudaSetDevice(device));
+  BrbModel *m = (BrbModel *)calloc(1, sizeof(BrbModel));
+  if (!m) return BRB_ENOMEM;
+  m->consts = *consts;
+  m->n_time = n_time;
+  m->device = device;
+  if (cudaMalloc(&m->time_table, sizeof(double) * n_time) != cudaSuccess) { free(m); return BRB_ENOMEM; }
+  if (cudaMemcpy(m->time_table, time_table_host, sizeof(double) * n_time, cudaMemcpyHostToDevice) != cudaSuccess) {
+    cudaFree(m->time_table); free(m); return BRB_ECUDA;
+  }
+  *out = m;
+  return BRB_OK;
+}
+
+extern "C" void brb_model_destroy(BrbModel *m) {
+  if (!m) return;
+  cudaFree(m->time_table);
+  free(m);
+}
+
+static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
+
+extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64_t env_id_offset, BrbEnv **out) {
+  if (!m || !out || n <= 0) return BRB_EINVAL;
+  CK(cudaSetDevice(m->device));
+  BrbEnv *e = (BrbEnv *)calloc(1, sizeof(BrbEnv));
+  if (!e) return BRB_ENOMEM;
+  e->model = m;
+  const size_t N = (size_t)n;
+  const size_t sz[] = {
+      align_up(9 * N * 8), align_up(8 * N * 8), align_up(4 * N * 8), align_up(8 * N * 4), align_up(N * 8), align_up(N * 8),
+      align_up(3 * N * 8), align_up(N * 4), align_up(N * 4), align_up(N * 4), align_up(BRB_NSTATS * 8),
+      // staging
+      align_up(2 * N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(N), align_up(N), align_up(N * 4)};
+  size_t total = 0;
+  for (size_t k = 0; k < sizeof(sz) / sizeof(sz[0]); k++) total += sz[k];
+  if (cudaMalloc(&e->arena, total) != cudaSuccess) { cudaGetLastError(); free(e); return BRB_ENOMEM; }
+  if (cudaMemset(e->arena, 0, total) != cudaSuccess) { cudaFree(e->arena); free(e); return BRB_ECUDA; }
+  char *p = (char *)e->arena;
+  int k = 0;
+#define TAKE(T) (T *)p; p += sz[k++]
+  e->S.qpos = TAKE(double);
+  e->S.qvel = TAKE(double);
+  e->S.xquat = TAKE(double);
+  e->S.warm = TAKE(float);
+  e->S.last_pitch = TAKE(double);
+  e->S.ep_return = TAKE(double);
+  e->S.v3 = TAKE(double);
+  e->S.elapsed = TAKE(int);
+  e->S.ep_len = TAKE(int);
+  e->S.event = TAKE(uint32_t);
+  e->S.stats = TAKE(unsigned long long);
+  e->d_actions = TAKE(float);
+  e->d_obs = TAKE(float);
+  e->d_reward = TAKE(float);
+  e->d_tobs = TAKE(float);
+  e->d_epret = TAKE(float);
+  e->d_done = TAKE(uint8_t);
+  e->d_trunc = TAKE(uint8_t);
+  e->d_eplen = TAKE(int32_t);
+#undef TAKE
+  e->S.n = n;
+  e->S.env0 = env_id_offset;
+  e->S.seed = seed;
+  e->S.time_table = m->time_table;
+  if (cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaFree(e->arena); free(e); return BRB_ECUDA; }
+  *out = e;
+  return BRB_OK;
+}
+
+extern "C" void brb_env_destroy(BrbEnv *e) {
+  if (!e) return;
+  cudaSetDevice(e->model->device);
+  cudaStreamDestroy(e->host_stream);
+  cudaFree(e->arena);
+  free(e);
+}
+
+extern "C" int64_t brb_env_num_envs(const BrbEnv *e) { return e ? e->S.n : 0; }
+extern "C" int64_t brb_env_num_launches(const BrbEnv *e) { return e ? e->launches : 0; }
+
+extern "C" int brb_env_reset_all(BrbEnv *e, float *obs, const double *replay_u_reset, void *stream) {
+  if (!e || !obs) return BRB_EINVAL;
+  CK(cudaSetDevice(e->model->device));
+  brb_launch_reset(e->model->consts.env_kind, &e->S, obs, replay_u_reset, (cudaStream_t)stream);
+  e->launches++;
+  CK(cudaGetLastError());
+  return BRB_OK;
+}
+
+extern "C" int brb_env_step(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,
+                            float *terminal_obs, float *ep_return, int32_t *ep_len, const double *replay_u, void *stream) {
+  if (!e || !actions || !obs) return BRB_EINVAL;
+  CK(cudaSetDevice(e->model->device));
+  brb_launch_step(e->model->consts.env_kind, &e->model->consts, &e->S, actions, obs, reward, done, truncated, terminal_obs,
+                  ep_return, ep_len, replay_u, (cudaStream_t)stream);
+  e->launches++;
+  CK(cudaGetLastError());
+  return BRB_OK;
+}
+
+extern "C" int brb_env_step_host(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,
+                                 float *terminal_obs, float *ep_return, int32_t *ep_len) {
+  if (!e || !actions || !obs) return BRB_EINVAL;
+  CK(cudaSetDevice(e->model->device));
+  const size_t N = (size_t)e->S.n;
+  cudaStream_t s = e->host_stream;
+  CK(cudaMemcpyAsync(e->d_actions, actions, 2 * N * sizeof(float), cudaMemcpyHostToDevice, s));
+  brb_launch_step(e->model->consts.env_kind, &e->model->consts, &e->S, e->d_actions, e->d_obs, e->d_reward, e->d_done, e->d_trunc,
+                  e->d_tobs, e->d_epret, e->d_eplen, nullptr, s);
+  e->launches++;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(obs, e->d_obs, 6 * N * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (reward) CK(cudaMemcpyAsync(reward, e->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (done) CK(cudaMemcpyAsync(done, e->d_done, N, cudaMemcpyDeviceToHost, s));
+  if (truncated) CK(cudaMemcpyAsync(truncated, e->d_trunc, N, cudaMemcpyDeviceToHost, s));
+  if (terminal_obs) CK(cudaMemcpyAsync(terminal_obs, e->d_tobs, 6 * N * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (ep_return) CK(cudaMemcpyAsync(ep_return, e->d_epret, N * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (ep_len) CK(cudaMemcpyAsync(ep_len, e->d_eplen, N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return BRB_OK;
+}
+
+extern "C" int brb_env_get_state(BrbEnv *e, double *qpos, double *qvel, double *xquat, void *stream) {
+  if (!e) return BRB_EINVAL;
+  CK(cudaSetDevice(e->model->device));
+  brb_launch_get_state(&e->S, qpos, qvel, xquat, (cudaStream_t)stream);
+  e->launches++;
+  CK(cudaGetLastError());
+  return BRB_OK;
+}
+
+extern "C" int brb_env_set_state(BrbEnv *e, const double *qpos, const double *qvel, void *stream) {
+  if (!e || !qpos || !qvel) return BRB_EINVAL;
+  CK(cudaSetDevice(e->model->device));
+  brb_launch_set_state(&e->S, qpos, qvel, (cudaStream_t)stream);
+  e->launches++;
+  CK(cudaGetLastError());
+  return BRB_OK;
+}
+
+extern "C" int brb_env_get_elapsed(BrbEnv *e, int32_t *elapsed, void *stream) {
+  if (!e || !elapsed) return BRB_EINVAL;
+  CK(cudaSetDevice(e->model->device));
+  brb_launch_get_elapsed(&e->S, elapsed, (cudaStream_t)stream);
+  e->launches++;
+  CK(cudaGetLastError());
+  return BRB_OK;
+}
+
+extern "C" int brb_env_get_stats(BrbEnv *e, uint64_t out[BRB_NSTATS]) {
+  if (!e || !out) return BRB_EINVAL;
+  CK(cudaSetDevice(e->model->device));
+  CK(cudaDeviceSynchronize());
+  CK(cudaMemcpy(out, e->S.stats, sizeof(uint64_t) * BRB_NSTATS, cudaMemcpyDeviceToHost));
+  return BRB_OK;
+}
+
+extern "C" int brb_fp32_peak_flops(int device, double *flops_out, double *ms_out) {
+  if (!flops_out) return BRB_EINVAL;
+  CK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  CK(cudaGetDeviceProperties(&prop, device));
+  const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 4096;
+  float *buf;
+  CK(cudaMalloc(&buf, sizeof(float) * (size_t)threads * blocks));
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 1e30;
+  for (int rep = 0; rep < 5; rep++) {
+    cudaEventRecord(e0, 0);
+    brb_launch_ffma_probe(buf, blocks, threads, iters, 0);
+    cudaEventRecord(e1, 0);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(buf); return BRB_ECUDA; }
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    if (rep > 0 && ms < best) best = ms;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cudaFree(buf);
+  const double flop = 2.0 * 8 * 16 * (double)iters * threads * blocks;
+  *flops_out = flop / (best * 1e-3);
+  if (ms_out) *ms_out = best;
+  return BRB_OK;
+}

@@ -1,0 +1,28 @@
+// brb_internal.h — device-side state layout shared by the kernels and the C-ABI translation unit.
+#ifndef BRB_INTERNAL_H
+#define BRB_INTERNAL_H
+#include <stdint.h>
+
+#define BRB_BLOCK 128   // threads per CTA of the step kernel (one env per thread)
+#define BRB_MAXIT 8     // cap on active-set (Newton) iterations per substep
+
+// Struct-of-arrays env state in HBM: column k of a [K][N] array lives at base + k*N, so a warp's 32
+// envs read 32 consecutive values of every column (fully coalesced 256 B / 128 B segments).
+struct BrbState {
+  long long n;            // envs in this shard
+  long long env0;         // global id of env 0 (Philox counter)
+  unsigned long long seed;
+  double *qpos;           // [9][N]  x y z qw qx qy qz thL thR        (MuJoCo data.qpos)
+  double *qvel;           // [8][N]  v_world(3) w_body(3) sL sR       (MuJoCo data.qvel)
+  double *xquat;          // [4][N]  chassis quaternion as the task logic sees it (one substep stale, Q1)
+  float *warm;            // [8][N]  chassis-frame solver acceleration of the last substep (qacc_warmstart)
+  double *last_pitch;     // [N]     RobotBaseEnv.last_pitch
+  double *ep_return;      // [N]     Monitor running return
+  double *v3;             // [3][N]  target_wheel_speed, delay_target_speed, pitch_offset (Env01-v3 only)
+  int *elapsed;           // [N]     TimeLimit._elapsed_steps (also indexes the time table)
+  int *ep_len;            // [N]
+  uint32_t *event;        // [N]     Philox event counter (0 = reset_all, k = k-th step call)
+  const double *time_table;  // [max_episode_steps + 2] fp64 data.time after k env steps
+  unsigned long long *stats; // [BRB_NSTATS]
+};
+#endif

@@ -1,0 +1,110 @@
+/*
+ * brb.h — C-ABI of the B200-native batched balance-robot environment step.
+ *
+ * This is the drop-in boundary for the reference's hot path.  The reference has no FFI of its own:
+ * the seam is the Gymnasium Env API consumed through SB3's VecEnv, i.e. the Python
+ * calls listed next to each entry point below.  All `*_dev` style pointers are DEVICE pointers
+ * (e.g. torch tensor .data_ptr()); `stream` is a cudaStream_t passed as void* (NULL = legacy default
+ * stream).  Every function returns 0 on success or a negative BRB_E* code; nothing throws; no CPU
+ * fallback exists — without a CUDA device every compute entry point returns BRB_ECUDA.
+ *
+ * Layouts: obs [N,6] f32 row-major; actions [N,2] f32; reward [N] f32; done/truncated [N] u8;
+ * terminal_obs [N,6] f32; ep_return [N] f32; ep_len [N] i32; qpos [N,9] f64; qvel [N,8] f64.
+ */
+#ifndef BRB_H
+#define BRB_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BRB_OK 0
+#define BRB_EINVAL (-22)
+#define BRB_ENOMEM (-12)
+#define BRB_ECUDA (-5)
+
+#define BRB_ENV01_V1 0 /* reference balance_robot/__init__.py:5-10  -> envs/env01_v1.py:10 */
+#define BRB_ENV01_V2 1 /* reference balance_robot/__init__.py:12-17 -> envs/env01_v2.py:14 */
+#define BRB_ENV01_V3 2 /* reference balance_robot/__init__.py:19-24 -> envs/env01_v3.py:13 */
+
+#define BRB_FLAG_ACTDERIV_SKIP_CLAMPED 1
+
+#define BRB_NSTATS 8
+#define BRB_STAT_SUBSTEPS 0          /* env-substeps executed */
+#define BRB_STAT_CONTACT_SUBSTEPS 1  /* of which had >= 1 wheel-floor contact */
+#define BRB_STAT_SOLVES 2            /* 8x8 factorisations performed */
+#define BRB_STAT_NONCONVERGED 3      /* substeps that hit the active-set iteration cap */
+#define BRB_STAT_UNSUPPORTED 4       /* env-steps that ended in a pose whose contacts the kernel does not model */
+#define BRB_STAT_EPISODES 5          /* episodes finished */
+#define BRB_STAT_ENV_STEPS 6
+
+/* Per-model constant block, produced on the host by balance_robot_b200/model.py from the MJCF
+ * (stands in for MjModel.from_xml_path, reference envs/RobotBaseEnv.py:56-65).  Passed to the
+ * kernels by value (constant bank). */
+typedef struct BrbModelConsts {
+  float h, grav, mass, mcz;
+  float Ixx, Iyy, Izz, Ia;
+  float minv_xy[3], minv_uz, minv_wz, minv_blk[10];
+  float ox, oz, rad, hl, zfloor, zfloor_lo; /* floor height = zfloor + zfloor_lo (hi/lo split of the fp64 value) */
+  float damping, kv, ctrl_lo, ctrl_hi, frc_lo, frc_hi;
+  float mu, D, Kimp, Bdamp;
+  float impl_W[8], impl_G[3], impl_cinv_full, impl_cinv_damp;
+  float chassis_half[3], chassis_pos[3];
+  int frame_skip, max_episode_steps, env_kind, flags;
+} BrbModelConsts;
+
+typedef struct BrbModel BrbModel;
+typedef struct BrbEnv BrbEnv;
+
+int brb_version(void);
+const char *brb_strerror(int code);
+
+/* MjModel.from_xml_path: uploads the constant block and the fp64 step-time table
+ * (time_table[k] = data.time after k env steps, k = 0..n_time-1). */
+int brb_model_create(const BrbModelConsts *consts, const double *time_table_host, int n_time, int device, BrbModel **out);
+void brb_model_destroy(BrbModel *m);
+
+/* gym.make(id) x n_envs (reference sb_rl.py:500).  env_id_offset = global id of env 0 of this shard, so
+ * the Philox streams are invariant to how envs are sharded across GPUs. */
+int brb_env_create(const BrbModel *m, int64_t n_envs, uint64_t seed, int64_t env_id_offset, BrbEnv **out);
+void brb_env_destroy(BrbEnv *e);
+
+/* VecEnv.reset() -> MujocoEnv.reset -> reset_model (reference envs/env01_v1.py:39-58, env01_v2.py:52-71,
+ * env01_v3.py:39-54).  replay_u_reset: optional [N,16] f64 uniforms replacing the Philox draws. */
+int brb_env_reset_all(BrbEnv *e, float *obs, const double *replay_u_reset, void *stream);
+
+/* VecEnv.step(actions) (DummyVecEnv auto-reset + TimeLimit + Monitor around reference
+ * envs/env01_v1.py:15-37 / env01_v2.py:28-50 / env01_v3.py:27-37, which call mujoco.mj_step x250).
+ * replay_u: optional [N,20] f64 uniforms (4 step-noise slots then 16 reset slots) replacing Philox.
+ * terminal_obs rows are written only where done; ep_return / ep_len hold the running episode
+ * statistics (the finished episode's totals where done). Any output pointer except obs may be NULL. */
+int brb_env_step(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,
+                 float *terminal_obs, float *ep_return, int32_t *ep_len, const double *replay_u, void *stream);
+
+/* Same call with HOST buffers (pinned or pageable): copies actions in, steps, copies results out and
+ * synchronises the stream.  This is the end-to-end path a host-side trainer (SB3 on CPU tensors) uses. */
+int brb_env_step_host(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,
+                      float *terminal_obs, float *ep_return, int32_t *ep_len);
+
+/* MujocoEnv.set_state / data.qpos, data.qvel access (trajectory checks).  xquat = the (stale, Q1) chassis
+ * quaternion the observation functions read; may be NULL. */
+int brb_env_get_state(BrbEnv *e, double *qpos, double *qvel, double *xquat, void *stream);
+int brb_env_set_state(BrbEnv *e, const double *qpos, const double *qvel, void *stream);
+/* per-env episode bookkeeping (elapsed steps); out [N] i32 */
+int brb_env_get_elapsed(BrbEnv *e, int32_t *elapsed, void *stream);
+
+/* Synchronises and copies the cumulative counters (BRB_STAT_*) to the host. */
+int brb_env_get_stats(BrbEnv *e, uint64_t out[BRB_NSTATS]);
+int64_t brb_env_num_envs(const BrbEnv *e);
+/* kernel launches issued so far by this env object (for bench.py's gpu_launches) */
+int64_t brb_env_num_launches(const BrbEnv *e);
+
+/* FP32-pipe peak probe: runs an FFMA-bound kernel and returns achieved FLOP/s (for the roofline denominator). */
+int brb_fp32_peak_flops(int device, double *flops_out, double *ms_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

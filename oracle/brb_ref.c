@@ -1,0 +1,702 @@
+/*
+ * brb_ref.c — fp64 CPU ORACLE (test infrastructure; see brb_ref.h for the usage rule and the
+ * "parity unpinned" statement).
+ *
+ * Restates, for the model class {free-joint root bodies, hinge children, plane/box/cylinder geoms,
+ * velocity servos, pyramidal condim-3 contacts, Newton solver, implicitfast}, what the reference
+ * obtains from mujoco.mj_step (reference envs/env01_v1.py:24, envs/env01_v2.py:37) with the model
+ * of envs/env01_v1.xml + envs/robot-02.xml.  Section numbers (A.x) refer to SURVEY.md Appendix A.
+ *
+ * The dynamics are computed with projected Newton-Euler sums over bodies in world coordinates
+ * (mass matrix = sum_b m Jv'Jv + Jw' I Jw, bias = sum_b Jv' m (a_vp - g) + Jw' (I alpha_vp + W x I W)),
+ * which yields the same M(q) and c(q,v) as MuJoCo's CRB / RNE.  It is deliberately a different
+ * algorithm from the body-frame closed form the CUDA kernel uses, so the two check each other.
+ */
+#include "brb_ref.h"
+
+#include <math.h>
+#include <string.h>
+
+#define MINVAL 1e-15
+#define MINIMP 0.0001
+#define MAXIMP 0.9999
+
+/* ------------------------------------------------------------------ small vector helpers */
+static inline double dot3(const double *a, const double *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+static inline void cross3(double *r, const double *a, const double *b) {
+  double x = a[1] * b[2] - a[2] * b[1], y = a[2] * b[0] - a[0] * b[2], z = a[0] * b[1] - a[1] * b[0];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+static inline void matvec3(double *r, const double *R, const double *v) { /* R row-major */
+  double x = R[0] * v[0] + R[1] * v[1] + R[2] * v[2];
+  double y = R[3] * v[0] + R[4] * v[1] + R[5] * v[2];
+  double z = R[6] * v[0] + R[7] * v[1] + R[8] * v[2];
+  r[0] = x; r[1] = y; r[2] = z;
+}
+static inline double normalize3(double *v) {
+  double n = sqrt(dot3(v, v));
+  if (n < MINVAL) { v[0] = 1; v[1] = 0; v[2] = 0; return 0.0; }
+  v[0] /= n; v[1] /= n; v[2] /= n;
+  return n;
+}
+static inline void normalize4(double *q) {
+  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  if (n < MINVAL) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  q[0] /= n; q[1] /= n; q[2] /= n; q[3] /= n;
+}
+static inline void mulquat(double *r, const double *a, const double *b) {
+  double w = a[0] * b[0] - a[1] * b[1] - a[2] * b[2] - a[3] * b[3];
+  double x = a[0] * b[1] + a[1] * b[0] + a[2] * b[3] - a[3] * b[2];
+  double y = a[0] * b[2] - a[1] * b[3] + a[2] * b[0] + a[3] * b[1];
+  double z = a[0] * b[3] + a[1] * b[2] - a[2] * b[1] + a[3] * b[0];
+  r[0] = w; r[1] = x; r[2] = y; r[3] = z;
+}
+static inline void quat2mat(double *R, const double *q) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  R[0] = w * w + x * x - y * y - z * z; R[1] = 2 * (x * y - w * z); R[2] = 2 * (x * z + w * y);
+  R[3] = 2 * (x * y + w * z); R[4] = w * w - x * x + y * y - z * z; R[5] = 2 * (y * z - w * x);
+  R[6] = 2 * (x * z - w * y); R[7] = 2 * (y * z + w * x); R[8] = w * w - x * x - y * y + z * z;
+}
+static inline void axisangle2quat(double *q, const double *axis, double angle) {
+  if (angle == 0) { q[0] = 1; q[1] = q[2] = q[3] = 0; return; }
+  double s = sin(angle * 0.5);
+  q[0] = cos(angle * 0.5); q[1] = axis[0] * s; q[2] = axis[1] * s; q[3] = axis[2] * s;
+}
+
+/* dense Cholesky of the leading n x n block of A (row stride ld); lower factor in place. 0 on success */
+static int chol_factor(double *A, int n, int ld) {
+  for (int j = 0; j < n; j++) {
+    double s = A[j * ld + j];
+    for (int k = 0; k < j; k++) s -= A[j * ld + k] * A[j * ld + k];
+    if (s <= 0) return -1;
+    s = sqrt(s);
+    A[j * ld + j] = s;
+    for (int i = j + 1; i < n; i++) {
+      double t = A[i * ld + j];
+      for (int k = 0; k < j; k++) t -= A[i * ld + k] * A[j * ld + k];
+      A[i * ld + j] = t / s;
+    }
+  }
+  return 0;
+}
+static void chol_solve(const double *L, int n, int ld, double *x) {
+  for (int i = 0; i < n; i++) {
+    double t = x[i];
+    for (int k = 0; k < i; k++) t -= L[i * ld + k] * x[k];
+    x[i] = t / L[i * ld + i];
+  }
+  for (int i = n - 1; i >= 0; i--) {
+    double t = x[i];
+    for (int k = i + 1; k < n; k++) t -= L[k * ld + i] * x[k];
+    x[i] = t / L[i * ld + i];
+  }
+}
+
+int brb_ref_sizeof_model(void) { return (int)sizeof(BrbRefModel); }
+int brb_ref_sizeof_data(void) { return (int)sizeof(BrbRefData); }
+int brb_ref_sizeof_contact(void) { return (int)sizeof(BrbRefContact); }
+
+/* ------------------------------------------------------------------ A.3 step 2: kinematics */
+void brb_ref_kinematics(const BrbRefModel *m, BrbRefData *d) {
+  memset(d->xpos[0], 0, sizeof d->xpos[0]);
+  d->xquat[0][0] = 1; d->xquat[0][1] = d->xquat[0][2] = d->xquat[0][3] = 0;
+  quat2mat(d->xmat[0], d->xquat[0]);
+  memset(d->xipos[0], 0, sizeof d->xipos[0]);
+  for (int b = 1; b < m->nbody; b++) {
+    int p = m->body_parent[b], j = m->body_jnt[b];
+    double *xp = d->xpos[b], *xq = d->xquat[b];
+    if (j >= 0 && m->jnt_type[j] == BRB_JNT_FREE) {
+      int a = m->jnt_qposadr[j];
+      memcpy(xp, d->qpos + a, 3 * sizeof(double));
+      memcpy(xq, d->qpos + a + 3, 4 * sizeof(double));
+      normalize4(xq);
+      memcpy(d->xanchor[j], xp, 3 * sizeof(double));
+      d->xaxis[j][0] = d->xaxis[j][1] = 0; d->xaxis[j][2] = 1;
+    } else {
+      double t[3];
+      matvec3(t, d->xmat[p], m->body_pos[b]);
+      for (int k = 0; k < 3; k++) xp[k] = d->xpos[p][k] + t[k];
+      mulquat(xq, d->xquat[p], m->body_quat[b]);
+      if (j >= 0) { /* hinge */
+        double R[9], qr[4], off[3];
+        quat2mat(R, xq);
+        matvec3(off, R, m->jnt_pos[j]);
+        for (int k = 0; k < 3; k++) d->xanchor[j][k] = xp[k] + off[k];
+        matvec3(d->xaxis[j], R, m->jnt_axis[j]);
+        int a = m->jnt_qposadr[j];
+        axisangle2quat(qr, m->jnt_axis[j], d->qpos[a] - m->qpos0[a]);
+        mulquat(xq, xq, qr);
+        quat2mat(R, xq);
+        matvec3(off, R, m->jnt_pos[j]);
+        for (int k = 0; k < 3; k++) xp[k] = d->xanchor[j][k] - off[k];
+      }
+      normalize4(xq);
+    }
+    quat2mat(d->xmat[b], xq);
+    double t[3];
+    matvec3(t, d->xmat[b], m->body_ipos[b]);
+    for (int k = 0; k < 3; k++) d->xipos[b][k] = xp[k] + t[k];
+  }
+  for (int g = 0; g < m->ngeom; g++) {
+    int b = m->geom_body[g];
+    double t[3], Rg[9];
+    matvec3(t, d->xmat[b], m->geom_pos[g]);
+    for (int k = 0; k < 3; k++) d->geom_xpos[g][k] = d->xpos[b][k] + t[k];
+    quat2mat(Rg, m->geom_quat[g]);
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < 3; c++)
+        d->geom_xmat[g][3 * r + c] = d->xmat[b][3 * r] * Rg[c] + d->xmat[b][3 * r + 1] * Rg[3 + c] + d->xmat[b][3 * r + 2] * Rg[6 + c];
+  }
+}
+
+/* A.7: point Jacobians in MuJoCo's dof convention (free joint: world-frame linear velocity of the
+ * body origin, BODY-frame angular velocity; hinge: rotation about the world-frame axis through the anchor) */
+void brb_ref_jac(const BrbRefModel *m, const BrbRefData *d, int body, const double p[3], double *jacp, double *jacr) {
+  int nv = m->nv;
+  if (jacp) memset(jacp, 0, 3 * nv * sizeof(double));
+  if (jacr) memset(jacr, 0, 3 * nv * sizeof(double));
+  for (int b = body; b > 0; b = m->body_parent[b]) {
+    int j = m->body_jnt[b];
+    if (j < 0) continue;
+    int a = m->jnt_dofadr[j];
+    if (m->jnt_type[j] == BRB_JNT_FREE) {
+      double r[3] = {p[0] - d->xpos[b][0], p[1] - d->xpos[b][1], p[2] - d->xpos[b][2]};
+      for (int k = 0; k < 3; k++) {
+        if (jacp) jacp[k * nv + a + k] = 1.0;
+        double col[3] = {d->xmat[b][k], d->xmat[b][3 + k], d->xmat[b][6 + k]}, c[3];
+        cross3(c, col, r);
+        for (int i = 0; i < 3; i++) {
+          if (jacr) jacr[i * nv + a + 3 + k] = col[i];
+          if (jacp) jacp[i * nv + a + 3 + k] = c[i];
+        }
+      }
+    } else {
+      double r[3] = {p[0] - d->xanchor[j][0], p[1] - d->xanchor[j][1], p[2] - d->xanchor[j][2]}, c[3];
+      cross3(c, d->xaxis[j], r);
+      for (int i = 0; i < 3; i++) {
+        if (jacr) jacr[i * nv + a] = d->xaxis[j][i];
+        if (jacp) jacp[i * nv + a] = c[i];
+      }
+    }
+  }
+}
+
+static void body_world_inertia(const BrbRefModel *m, const BrbRefData *d, int b, double *Iw) {
+  const double *R = d->xmat[b], *I = m->body_inertia[b];
+  double T[9];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) T[3 * r + c] = R[3 * r] * I[c] + R[3 * r + 1] * I[3 + c] + R[3 * r + 2] * I[6 + c];
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 3; c++) Iw[3 * r + c] = T[3 * r] * R[3 * c] + T[3 * r + 1] * R[3 * c + 1] + T[3 * r + 2] * R[3 * c + 2];
+}
+
+/* A.3 step 3: joint-space inertia M(q), dense nv x nv (row stride BRB_MAXNV) */
+void brb_ref_mass_matrix(const BrbRefModel *m, BrbRefData *d) {
+  int nv = m->nv;
+  double jp[3 * BRB_MAXNV], jr[3 * BRB_MAXNV], Iw[9], IJ[3 * BRB_MAXNV];
+  memset(d->qM, 0, sizeof d->qM);
+  for (int b = 1; b < m->nbody; b++) {
+    brb_ref_jac(m, d, b, d->xipos[b], jp, jr);
+    body_world_inertia(m, d, b, Iw);
+    for (int r = 0; r < 3; r++)
+      for (int c = 0; c < nv; c++) IJ[r * nv + c] = Iw[3 * r] * jr[c] + Iw[3 * r + 1] * jr[nv + c] + Iw[3 * r + 2] * jr[2 * nv + c];
+    for (int i = 0; i < nv; i++)
+      for (int k = 0; k < nv; k++) {
+        double s = 0;
+        for (int r = 0; r < 3; r++) s += m->body_mass[b] * jp[r * nv + i] * jp[r * nv + k] + jr[r * nv + i] * IJ[r * nv + k];
+        d->qM[i * BRB_MAXNV + k] += s;
+      }
+  }
+}
+
+/* A.3 step 4: qfrc_bias = C(q,v) v + G(q) via velocity-product accelerations (qacc = 0) */
+void brb_ref_bias(const BrbRefModel *m, BrbRefData *d) {
+  int nv = m->nv;
+  double W[BRB_MAXBODY][3], Al[BRB_MAXBODY][3], aO[BRB_MAXBODY][3];
+  double jp[3 * BRB_MAXNV], jr[3 * BRB_MAXNV], Iw[9];
+  memset(d->qfrc_bias, 0, sizeof d->qfrc_bias);
+  memset(W, 0, sizeof W); memset(Al, 0, sizeof Al); memset(aO, 0, sizeof aO);
+  for (int b = 1; b < m->nbody; b++) {
+    int p = m->body_parent[b], j = m->body_jnt[b];
+    if (j >= 0 && m->jnt_type[j] == BRB_JNT_FREE) {
+      int a = m->jnt_dofadr[j];
+      matvec3(W[b], d->xmat[b], d->qvel + a + 3); /* world angular velocity; alpha_vp = 0, a_origin_vp = 0 */
+    } else {
+      double ra[3], t[3], t2[3], aa[3];
+      const double *anchor = (j >= 0) ? d->xanchor[j] : d->xpos[b];
+      for (int k = 0; k < 3; k++) ra[k] = anchor[k] - d->xpos[p][k];
+      cross3(t, Al[p], ra);
+      cross3(t2, W[p], ra); cross3(t2, W[p], t2);
+      for (int k = 0; k < 3; k++) aa[k] = aO[p][k] + t[k] + t2[k];
+      memcpy(W[b], W[p], sizeof W[b]); memcpy(Al[b], Al[p], sizeof Al[b]);
+      if (j >= 0) {
+        double qd = d->qvel[m->jnt_dofadr[j]], wxa[3];
+        cross3(wxa, W[p], d->xaxis[j]);
+        for (int k = 0; k < 3; k++) { W[b][k] += d->xaxis[j][k] * qd; Al[b][k] += wxa[k] * qd; }
+      }
+      double ro[3];
+      for (int k = 0; k < 3; k++) ro[k] = d->xpos[b][k] - anchor[k];
+      cross3(t, Al[b], ro);
+      cross3(t2, W[b], ro); cross3(t2, W[b], t2);
+      for (int k = 0; k < 3; k++) aO[b][k] = aa[k] + t[k] + t2[k];
+    }
+    double rc[3], t[3], t2[3], F[3], N[3], IW[3], IA[3];
+    for (int k = 0; k < 3; k++) rc[k] = d->xipos[b][k] - d->xpos[b][k];
+    cross3(t, Al[b], rc);
+    cross3(t2, W[b], rc); cross3(t2, W[b], t2);
+    for (int k = 0; k < 3; k++) F[k] = m->body_mass[b] * (aO[b][k] + t[k] + t2[k] - m->gravity[k]);
+    body_world_inertia(m, d, b, Iw);
+    matvec3(IW, Iw, W[b]); matvec3(IA, Iw, Al[b]);
+    cross3(N, W[b], IW);
+    for (int k = 0; k < 3; k++) N[k] += IA[k];
+    brb_ref_jac(m, d, b, d->xipos[b], jp, jr);
+    for (int c = 0; c < nv; c++)
+      for (int r = 0; r < 3; r++) d->qfrc_bias[c] += jp[r * nv + c] * F[r] + jr[r * nv + c] * N[r];
+  }
+}
+
+double brb_ref_energy(const BrbRefModel *m, BrbRefData *d, double *kinetic, double *potential) {
+  brb_ref_kinematics(m, d);
+  brb_ref_mass_matrix(m, d);
+  double ke = 0, pe = 0;
+  for (int i = 0; i < m->nv; i++)
+    for (int k = 0; k < m->nv; k++) ke += 0.5 * d->qvel[i] * d->qM[i * BRB_MAXNV + k] * d->qvel[k];
+  for (int b = 1; b < m->nbody; b++) pe -= m->body_mass[b] * dot3(m->gravity, d->xipos[b]);
+  if (kinetic) *kinetic = ke;
+  if (potential) *potential = pe;
+  return ke + pe;
+}
+
+/* ------------------------------------------------------------------ mj_setConst restatement */
+int brb_ref_model_finalize(BrbRefModel *m) {
+  static BrbRefData d; /* large; finalize is called once per model from one thread */
+  memset(&d, 0, sizeof d);
+  memset(m->qpos0, 0, sizeof m->qpos0);
+  for (int j = 0; j < m->njnt; j++)
+    if (m->jnt_type[j] == BRB_JNT_FREE) {
+      int a = m->jnt_qposadr[j], b = m->jnt_body[j];
+      for (int k = 0; k < 3; k++) m->qpos0[a + k] = m->body_pos[b][k];
+      for (int k = 0; k < 4; k++) m->qpos0[a + 3 + k] = m->body_quat[b][k];
+    }
+  if (m->solver_tolerance <= 0) m->solver_tolerance = 1e-13;
+  memcpy(d.qpos, m->qpos0, sizeof d.qpos);
+  brb_ref_kinematics(m, &d);
+  brb_ref_mass_matrix(m, &d);
+  int nv = m->nv;
+  double tr = 0;
+  for (int i = 0; i < nv; i++) tr += d.qM[i * BRB_MAXNV + i];
+  m->meaninertia = tr / nv;
+  double L[BRB_MAXNV * BRB_MAXNV];
+  memcpy(L, d.qM, sizeof L);
+  if (chol_factor(L, nv, BRB_MAXNV)) return -1;
+  m->body_invweight0[0][0] = m->body_invweight0[0][1] = 0;
+  for (int b = 1; b < m->nbody; b++) {
+    double jp[3 * BRB_MAXNV], jr[3 * BRB_MAXNV], col[BRB_MAXNV];
+    brb_ref_jac(m, &d, b, d.xipos[b], jp, jr);
+    double tt = 0, rr = 0;
+    for (int r = 0; r < 3; r++) {
+      memcpy(col, jp + r * nv, nv * sizeof(double));
+      chol_solve(L, nv, BRB_MAXNV, col);
+      for (int c = 0; c < nv; c++) tt += jp[r * nv + c] * col[c];
+      memcpy(col, jr + r * nv, nv * sizeof(double));
+      chol_solve(L, nv, BRB_MAXNV, col);
+      for (int c = 0; c < nv; c++) rr += jr[r * nv + c] * col[c];
+    }
+    m->body_invweight0[b][0] = tt / 3 > MINVAL ? tt / 3 : MINVAL;
+    m->body_invweight0[b][1] = rr / 3 > MINVAL ? rr / 3 : MINVAL;
+  }
+  return 0;
+}
+
+void brb_ref_reset_data(const BrbRefModel *m, BrbRefData *d) {
+  memset(d, 0, sizeof *d);
+  memcpy(d->qpos, m->qpos0, sizeof d->qpos);
+}
+
+/* ------------------------------------------------------------------ A.6 colliders */
+static BrbRefContact *new_contact(BrbRefData *d, const BrbRefModel *m, int pair, double dist, const double *pos, const double *normal) {
+  if (d->ncon >= BRB_MAXCON) return 0;
+  BrbRefContact *c = &d->contact[d->ncon++];
+  memset(c, 0, sizeof *c);
+  c->dist = dist;
+  memcpy(c->pos, pos, 3 * sizeof(double));
+  memcpy(c->frame, normal, 3 * sizeof(double));
+  c->pair = pair;
+  c->dim = m->pair_condim[pair];
+  c->body1 = m->geom_body[m->pair_geom1[pair]];
+  c->body2 = m->geom_body[m->pair_geom2[pair]];
+  c->includemargin = m->pair_margin[pair] - m->pair_gap[pair];
+  memcpy(c->friction, m->pair_friction[pair], sizeof c->friction);
+  memcpy(c->solref, m->pair_solref[pair], sizeof c->solref);
+  memcpy(c->solimp, m->pair_solimp[pair], sizeof c->solimp);
+  return c;
+}
+
+static void collide_plane_cylinder(const BrbRefModel *m, BrbRefData *d, int pair) {
+  int g1 = m->pair_geom1[pair], g2 = m->pair_geom2[pair];
+  const double *mat1 = d->geom_xmat[g1], *mat2 = d->geom_xmat[g2], *pos1 = d->geom_xpos[g1], *pos2 = d->geom_xpos[g2];
+  double margin = m->pair_margin[pair], radius = m->geom_size[g2][0], halflen = m->geom_size[g2][1];
+  double n[3] = {mat1[2], mat1[5], mat1[8]}, a[3] = {mat2[2], mat2[5], mat2[8]}, v[3], pos[3];
+  double prjaxis = dot3(n, a);
+  if (prjaxis > 0) { a[0] = -a[0]; a[1] = -a[1]; a[2] = -a[2]; prjaxis = -prjaxis; }
+  double rel[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  double dist0 = dot3(n, rel);
+  for (int k = 0; k < 3; k++) v[k] = a[k] * prjaxis - n[k];
+  double len2 = dot3(v, v);
+  if (len2 >= MINVAL * MINVAL) {
+    double s = radius / sqrt(len2);
+    for (int k = 0; k < 3; k++) v[k] *= s;
+  } else {
+    v[0] = mat2[0] * radius; v[1] = mat2[3] * radius; v[2] = mat2[6] * radius;
+  }
+  double prjvec = dot3(v, n);
+  for (int k = 0; k < 3; k++) a[k] *= halflen;
+  prjaxis *= halflen;
+  double dist = dist0 + prjaxis + prjvec;
+  if (dist > margin) return;
+  for (int k = 0; k < 3; k++) pos[k] = pos2[k] + v[k] + a[k] - n[k] * dist * 0.5;
+  new_contact(d, m, pair, dist, pos, n);
+  dist = dist0 - prjaxis + prjvec;
+  if (dist <= margin) {
+    for (int k = 0; k < 3; k++) pos[k] = pos2[k] + v[k] - a[k] - n[k] * dist * 0.5;
+    new_contact(d, m, pair, dist, pos, n);
+  }
+  double prjvec1 = -prjvec * 0.5;
+  dist = dist0 + prjaxis + prjvec1;
+  if (dist <= margin) {
+    double s[3];
+    cross3(s, v, a);
+    normalize3(s);
+    double sc = radius * sqrt(3.0) * 0.5;
+    for (int sign = 1; sign >= -1; sign -= 2) {
+      for (int k = 0; k < 3; k++) pos[k] = pos2[k] + sign * sc * s[k] + a[k] - v[k] * 0.5 - n[k] * dist * 0.5;
+      new_contact(d, m, pair, dist, pos, n);
+    }
+  }
+}
+
+static void collide_plane_box(const BrbRefModel *m, BrbRefData *d, int pair) {
+  int g1 = m->pair_geom1[pair], g2 = m->pair_geom2[pair];
+  const double *mat1 = d->geom_xmat[g1], *mat2 = d->geom_xmat[g2], *pos1 = d->geom_xpos[g1], *pos2 = d->geom_xpos[g2];
+  double margin = m->pair_margin[pair];
+  const double *size = m->geom_size[g2];
+  double n[3] = {mat1[2], mat1[5], mat1[8]};
+  double rel[3] = {pos2[0] - pos1[0], pos2[1] - pos1[1], pos2[2] - pos1[2]};
+  double dist0 = dot3(n, rel);
+  int cnt = 0;
+  for (int i = 0; i < 8; i++) {
+    double vec[3] = {(i & 1 ? size[0] : -size[0]), (i & 2 ? size[1] : -size[1]), (i & 4 ? size[2] : -size[2])}, corner[3], pos[3];
+    matvec3(corner, mat2, vec);
+    double ldist = dot3(n, corner);
+    if (dist0 + ldist > margin || ldist > 0) continue;
+    double dist = dist0 + ldist;
+    for (int k = 0; k < 3; k++) pos[k] = corner[k] + pos2[k] - n[k] * dist * 0.5;
+    new_contact(d, m, pair, dist, pos, n);
+    if (++cnt >= 4) return;
+  }
+}
+
+static void make_frame(double *f) { /* mju_makeFrame with an undefined y axis */
+  normalize3(f);
+  f[3] = f[4] = f[5] = 0;
+  if (f[1] < 0.5 && f[1] > -0.5) f[4] = 1; else f[5] = 1;
+  double t = dot3(f, f + 3);
+  for (int k = 0; k < 3; k++) f[3 + k] -= t * f[k];
+  normalize3(f + 3);
+  cross3(f + 6, f, f + 3);
+}
+
+static void collision(const BrbRefModel *m, BrbRefData *d) {
+  d->ncon = 0;
+  for (int p = 0; p < m->npair; p++) {
+    int t1 = m->geom_type[m->pair_geom1[p]], t2 = m->geom_type[m->pair_geom2[p]];
+    if (t1 == BRB_GEOM_PLANE && t2 == BRB_GEOM_CYLINDER) collide_plane_cylinder(m, d, p);
+    else if (t1 == BRB_GEOM_PLANE && t2 == BRB_GEOM_BOX) collide_plane_box(m, d, p);
+    /* box-box and cylinder-box (Env03 block) are not restated yet: SURVEY.md 8(f) row f2 */
+  }
+  for (int i = 0; i < d->ncon; i++) make_frame(d->contact[i].frame);
+}
+
+/* ------------------------------------------------------------------ A.7 constraint rows */
+static double get_impedance(const double *solimp_in, double pos, double margin) {
+  double s[5];
+  memcpy(s, solimp_in, sizeof s);
+  s[0] = fmin(MAXIMP, fmax(MINIMP, s[0])); s[1] = fmin(MAXIMP, fmax(MINIMP, s[1]));
+  s[2] = fmax(0, s[2]); s[3] = fmin(MAXIMP, fmax(MINIMP, s[3])); s[4] = fmax(1, s[4]);
+  if (s[0] == s[1] || s[2] <= MINVAL) return 0.5 * (s[0] + s[1]);
+  double x = (pos - margin) / s[2];
+  if (x < 0) x = -x;
+  if (x >= 1) return s[1];
+  if (x <= 0) return s[0];
+  double y;
+  if (s[4] == 1) y = x;
+  else if (x <= s[3]) y = pow(x, s[4]) / pow(s[3], s[4] - 1);
+  else y = 1 - pow(1 - x, s[4]) / pow(1 - s[3], s[4] - 1);
+  return s[0] + y * (s[1] - s[0]);
+}
+
+static void make_constraint(const BrbRefModel *m, BrbRefData *d) {
+  int nv = m->nv;
+  d->nefc = 0;
+  double jp1[3 * BRB_MAXNV], jp2[3 * BRB_MAXNV], jc[3 * BRB_MAXNV];
+  for (int ci = 0; ci < d->ncon; ci++) {
+    BrbRefContact *c = &d->contact[ci];
+    c->exclude = (c->dist >= c->includemargin);
+    c->efc_address = -1;
+    if (c->exclude) continue;
+    int nrow = (c->dim == 1) ? 1 : 2 * (c->dim - 1);
+    if (c->dim != 1 && c->dim != 3) continue; /* only condim 1 and 3 occur in the supported scenes */
+    if (d->nefc + nrow > BRB_MAXEFC) break;
+    brb_ref_jac(m, d, c->body1, c->pos, jp1, 0);
+    brb_ref_jac(m, d, c->body2, c->pos, jp2, 0);
+    for (int r = 0; r < 3; r++)
+      for (int k = 0; k < nv; k++) {
+        double s = 0;
+        for (int i = 0; i < 3; i++) s += c->frame[3 * r + i] * (jp2[i * nv + k] - jp1[i * nv + k]);
+        jc[r * nv + k] = s;
+      }
+    c->efc_address = d->nefc;
+    double tran = m->body_invweight0[c->body1][0] + m->body_invweight0[c->body2][0];
+    double imp = get_impedance(c->solimp, c->dist, c->includemargin);
+    /* reference accel parameters (standard solref, refsafe on) */
+    double tc = c->solref[0], dr = c->solref[1], dmax = fmin(MAXIMP, fmax(MINIMP, c->solimp[1])), K, B;
+    if (tc > 0) {
+      tc = fmax(tc, 2 * m->timestep);
+      K = 1.0 / fmax(MINVAL, dmax * dmax * tc * tc * dr * dr);
+      B = 2.0 / fmax(MINVAL, dmax * tc);
+    } else {
+      K = -tc / fmax(MINVAL, dmax * dmax);
+      B = -dr / fmax(MINVAL, dmax);
+    }
+    double R0 = 0;
+    for (int r = 0; r < nrow; r++) {
+      int e = d->nefc + r;
+      double *J = d->efc_J + e * BRB_MAXNV;
+      double diag;
+      if (c->dim == 1) {
+        memcpy(J, jc, nv * sizeof(double));
+        diag = tran;
+      } else {
+        double mu = c->friction[r / 2], sg = (r & 1) ? -1.0 : 1.0;
+        const double *jt = jc + (1 + r / 2) * nv;
+        for (int k = 0; k < nv; k++) J[k] = jc[k] + sg * mu * jt[k];
+        diag = tran * (1 + mu * mu);
+      }
+      double Rr = fmax(MINVAL, (1 - imp) / imp * diag);
+      if (r == 0) R0 = (m->flags & BRB_FLAG_RPY_FROM_FIRST_ROW) ? Rr : fmax(MINVAL, (1 - imp) / imp * tran);
+      if (c->dim > 1) Rr = 2 * c->friction[0] * c->friction[0] * R0;
+      d->efc_R[e] = Rr;
+      d->efc_D[e] = 1.0 / Rr;
+      d->efc_pos[e] = c->dist;
+      d->efc_margin[e] = c->includemargin;
+      double vel = 0;
+      for (int k = 0; k < nv; k++) vel += J[k] * d->qvel[k];
+      d->efc_vel[e] = vel;
+      d->efc_aref[e] = -B * vel - K * imp * (c->dist - c->includemargin);
+    }
+    d->nefc += nrow;
+  }
+}
+
+/* ------------------------------------------------------------------ A.8 Newton solver (primal) */
+static double solver_cost(const BrbRefModel *m, const BrbRefData *d, const double *a) {
+  int nv = m->nv;
+  double cost = 0, da[BRB_MAXNV];
+  for (int i = 0; i < nv; i++) da[i] = a[i] - d->qacc_smooth[i];
+  for (int i = 0; i < nv; i++)
+    for (int k = 0; k < nv; k++) cost += 0.5 * da[i] * d->qM[i * BRB_MAXNV + k] * da[k];
+  for (int e = 0; e < d->nefc; e++) {
+    double jar = -d->efc_aref[e];
+    for (int k = 0; k < nv; k++) jar += d->efc_J[e * BRB_MAXNV + k] * a[k];
+    if (jar < 0) cost += 0.5 * d->efc_D[e] * jar * jar;
+  }
+  return cost;
+}
+
+static void solve_constraints(const BrbRefModel *m, BrbRefData *d) {
+  int nv = m->nv, ne = d->nefc;
+  double a[BRB_MAXNV];
+  d->solver_niter = 0;
+  memset(d->qfrc_constraint, 0, sizeof d->qfrc_constraint);
+  if (ne == 0) {
+    memcpy(d->qacc, d->qacc_smooth, sizeof d->qacc);
+    return;
+  }
+  /* start from the better of warm start and unconstrained acceleration */
+  if (solver_cost(m, d, d->qacc_warmstart) < solver_cost(m, d, d->qacc_smooth)) memcpy(a, d->qacc_warmstart, sizeof a);
+  else memcpy(a, d->qacc_smooth, sizeof a);
+  double scale = 1.0 / (m->meaninertia * (nv > 1 ? nv : 1));
+  double jar[BRB_MAXEFC], jp[BRB_MAXEFC], g[BRB_MAXNV], p[BRB_MAXNV], H[BRB_MAXNV * BRB_MAXNV];
+  unsigned char act[BRB_MAXEFC];
+  for (int it = 0; it < 100; it++) {
+    for (int e = 0; e < ne; e++) {
+      double s = -d->efc_aref[e];
+      for (int k = 0; k < nv; k++) s += d->efc_J[e * BRB_MAXNV + k] * a[k];
+      jar[e] = s;
+      act[e] = s < 0;
+    }
+    /* gradient g = M (a - a_smooth) + J' D jar_active */
+    double gn = 0;
+    for (int i = 0; i < nv; i++) {
+      double s = 0;
+      for (int k = 0; k < nv; k++) s += d->qM[i * BRB_MAXNV + k] * (a[k] - d->qacc_smooth[k]);
+      for (int e = 0; e < ne; e++)
+        if (act[e]) s += d->efc_J[e * BRB_MAXNV + i] * d->efc_D[e] * jar[e];
+      g[i] = s;
+      gn += s * s;
+    }
+    if (scale * sqrt(gn) < m->solver_tolerance) break;
+    d->solver_niter++;
+    /* Hessian H = M + J' D_active J; Newton direction p = -H^-1 g */
+    memcpy(H, d->qM, sizeof H);
+    for (int e = 0; e < ne; e++)
+      if (act[e]) {
+        const double *J = d->efc_J + e * BRB_MAXNV;
+        for (int i = 0; i < nv; i++) {
+          double s = d->efc_D[e] * J[i];
+          if (s == 0) continue;
+          for (int k = 0; k <= i; k++) H[i * BRB_MAXNV + k] += s * J[k];
+        }
+      }
+    if (chol_factor(H, nv, BRB_MAXNV)) break;
+    for (int i = 0; i < nv; i++) p[i] = -g[i];
+    chol_solve(H, nv, BRB_MAXNV, p);
+    for (int e = 0; e < ne; e++) {
+      double s = 0;
+      for (int k = 0; k < nv; k++) s += d->efc_J[e * BRB_MAXNV + k] * p[k];
+      jp[e] = s;
+    }
+    /* full step keeps the active set -> exact minimiser of the (locally quadratic) cost: done */
+    int same = 1;
+    for (int e = 0; e < ne; e++)
+      if ((jar[e] + jp[e] < 0) != act[e]) { same = 0; break; }
+    if (same) {
+      for (int i = 0; i < nv; i++) a[i] += p[i];
+      break; /* consistent active set + full Newton step = exact minimiser */
+    }
+    /* exact line search on the piecewise-quadratic cost: root of the increasing piecewise-linear phi' */
+    double pMp = 0, pMd = 0;
+    for (int i = 0; i < nv; i++) {
+      double s = 0;
+      for (int k = 0; k < nv; k++) s += d->qM[i * BRB_MAXNV + k] * p[k];
+      pMp += p[i] * s;
+      pMd += s * (a[i] - d->qacc_smooth[i]);
+    }
+    double bp[BRB_MAXEFC + 1];
+    int nb = 0;
+    for (int e = 0; e < ne; e++)
+      if (jp[e] != 0) {
+        double t = -jar[e] / jp[e];
+        if (t > 0) bp[nb++] = t;
+      }
+    for (int i = 1; i < nb; i++) { /* insertion sort */
+      double t = bp[i];
+      int k = i - 1;
+      while (k >= 0 && bp[k] > t) { bp[k + 1] = bp[k]; k--; }
+      bp[k + 1] = t;
+    }
+    double lo = 0, alpha = 1;
+    for (int seg = 0; seg <= nb; seg++) {
+      double hi = (seg < nb) ? bp[seg] : -1;
+      double mid = (seg < nb) ? 0.5 * (lo + hi) : lo + 1.0;
+      double c0 = pMd, c1 = pMp;
+      for (int e = 0; e < ne; e++)
+        if (jar[e] + mid * jp[e] < 0) { c0 += d->efc_D[e] * jar[e] * jp[e]; c1 += d->efc_D[e] * jp[e] * jp[e]; }
+      double root = -c0 / c1;
+      if (seg == nb || root <= hi) { alpha = root < lo ? lo : root; break; }
+      lo = hi;
+    }
+    for (int i = 0; i < nv; i++) a[i] += alpha * p[i];
+  }
+  memcpy(d->qacc, a, sizeof a);
+  for (int e = 0; e < ne; e++) {
+    double s = -d->efc_aref[e];
+    for (int k = 0; k < nv; k++) s += d->efc_J[e * BRB_MAXNV + k] * a[k];
+    d->efc_force[e] = s < 0 ? -d->efc_D[e] * s : 0;
+    if (d->efc_force[e] != 0)
+      for (int k = 0; k < nv; k++) d->qfrc_constraint[k] += d->efc_J[e * BRB_MAXNV + k] * d->efc_force[e];
+  }
+}
+
+/* ------------------------------------------------------------------ mj_forward */
+static void forward_impl(const BrbRefModel *m, BrbRefData *d, double *Lm) {
+  int nv = m->nv;
+  brb_ref_kinematics(m, d);
+  brb_ref_mass_matrix(m, d);
+  memcpy(Lm, d->qM, sizeof(double) * BRB_MAXNV * BRB_MAXNV);
+  chol_factor(Lm, nv, BRB_MAXNV);
+  collision(m, d);
+  /* velocity stage */
+  memset(d->qfrc_passive, 0, sizeof d->qfrc_passive);
+  for (int j = 0; j < m->njnt; j++)
+    if (m->jnt_type[j] == BRB_JNT_HINGE) d->qfrc_passive[m->jnt_dofadr[j]] = -m->jnt_damping[j] * d->qvel[m->jnt_dofadr[j]];
+  brb_ref_bias(m, d);
+  /* actuation (A.3 step 5, Q7) */
+  memset(d->qfrc_actuator, 0, sizeof d->qfrc_actuator);
+  for (int u = 0; u < m->nu; u++) {
+    int dof = m->jnt_dofadr[m->act_jnt[u]];
+    double c = d->ctrl[u];
+    if (m->act_ctrllimited[u]) c = fmin(m->act_ctrlrange[u][1], fmax(m->act_ctrlrange[u][0], c));
+    double f = m->act_kv[u] * c - m->act_kv[u] * (m->act_gear[u] * d->qvel[dof]);
+    if (m->act_forcelimited[u]) f = fmin(m->act_forcerange[u][1], fmax(m->act_forcerange[u][0], f));
+    d->actuator_force[u] = f;
+    d->qfrc_actuator[dof] += m->act_gear[u] * f;
+  }
+  for (int i = 0; i < nv; i++) {
+    d->qfrc_smooth[i] = d->qfrc_passive[i] - d->qfrc_bias[i] + d->qfrc_actuator[i];
+    d->qacc_smooth[i] = d->qfrc_smooth[i];
+  }
+  chol_solve(Lm, nv, BRB_MAXNV, d->qacc_smooth);
+  make_constraint(m, d);
+  solve_constraints(m, d);
+  memcpy(d->qacc_warmstart, d->qacc, sizeof d->qacc);
+}
+
+void brb_ref_forward(const BrbRefModel *m, BrbRefData *d) {
+  double Lm[BRB_MAXNV * BRB_MAXNV];
+  forward_impl(m, d, Lm);
+}
+
+/* ------------------------------------------------------------------ A.9 / A.10: implicitfast + advance */
+void brb_ref_step(const BrbRefModel *m, BrbRefData *d, int nstep) {
+  int nv = m->nv;
+  double h = m->timestep;
+  double Lm[BRB_MAXNV * BRB_MAXNV], A[BRB_MAXNV * BRB_MAXNV], qacc[BRB_MAXNV];
+  for (int s = 0; s < nstep; s++) {
+    forward_impl(m, d, Lm);
+    d->stat_substeps++;
+    d->stat_contact_substeps += d->nefc > 0;
+    d->stat_newton_iters += d->solver_niter;
+    d->stat_efc_rows += d->nefc;
+    /* (M - h dF/dv) a+ = qfrc_smooth + qfrc_constraint; dF/dv = passive damping + actuator bias */
+    memcpy(A, d->qM, sizeof A);
+    for (int j = 0; j < m->njnt; j++)
+      if (m->jnt_type[j] == BRB_JNT_HINGE) A[m->jnt_dofadr[j] * (BRB_MAXNV + 1)] += h * m->jnt_damping[j];
+    for (int u = 0; u < m->nu; u++) {
+      int dof = m->jnt_dofadr[m->act_jnt[u]];
+      if ((m->flags & BRB_FLAG_ACTDERIV_SKIP_CLAMPED) && m->act_forcelimited[u] &&
+          (d->actuator_force[u] <= m->act_forcerange[u][0] || d->actuator_force[u] >= m->act_forcerange[u][1]))
+        continue;
+      A[dof * (BRB_MAXNV + 1)] += h * m->act_kv[u] * m->act_gear[u] * m->act_gear[u];
+    }
+    chol_factor(A, nv, BRB_MAXNV);
+    for (int i = 0; i < nv; i++) qacc[i] = d->qfrc_smooth[i] + d->qfrc_constraint[i];
+    chol_solve(A, nv, BRB_MAXNV, qacc);
+    /* mj_advance: velocity first, then positions with the NEW velocity */
+    for (int i = 0; i < nv; i++) d->qvel[i] += h * qacc[i];
+    for (int j = 0; j < m->njnt; j++) {
+      int qa = m->jnt_qposadr[j], da = m->jnt_dofadr[j];
+      if (m->jnt_type[j] == BRB_JNT_FREE) {
+        for (int k = 0; k < 3; k++) d->qpos[qa + k] += h * d->qvel[da + k];
+        double w[3] = {d->qvel[da + 3], d->qvel[da + 4], d->qvel[da + 5]}, qr[4];
+        double ang = h * normalize3(w);
+        axisangle2quat(qr, w, ang);
+        normalize4(d->qpos + qa + 3);
+        mulquat(d->qpos + qa + 3, d->qpos + qa + 3, qr);
+      } else {
+        d->qpos[qa] += h * d->qvel[da];
+      }
+    }
+    d->time += h;
+  }
+}

@@ -1,0 +1,84 @@
+// emu.cpp — TEST-ONLY host harness around the CUDA kernels' per-env functions (compiled with -DBRB_HOST_EMU).
+// Not part of the product; never shipped in libbrb_cuda.so.
+#include <stdlib.h>
+#include <string.h>
+#include "../../balance_robot_b200/csrc/brb_kernels.cu"
+
+struct Emu {
+  BrbModelConsts c;
+  BrbState S;
+  double *tt;
+  unsigned long long stats[BRB_NSTATS];
+};
+
+extern "C" Emu *emu_create(const BrbModelConsts *c, const double *tt, int n_time, long long n, unsigned long long seed, long long env0) {
+  Emu *e = (Emu *)calloc(1, sizeof(Emu));
+  e->c = *c;
+  e->tt = (double *)malloc(sizeof(double) * n_time);
+  memcpy(e->tt, tt, sizeof(double) * n_time);
+  BrbState &S = e->S;
+  S.n = n; S.env0 = env0; S.seed = seed;
+  S.qpos = (double *)calloc(9 * n, 8); S.qvel = (double *)calloc(8 * n, 8); S.xquat = (double *)calloc(4 * n, 8);
+  S.warm = (float *)calloc(8 * n, 4); S.last_pitch = (double *)calloc(n, 8); S.ep_return = (double *)calloc(n, 8);
+  S.v3 = (double *)calloc(3 * n, 8); S.elapsed = (int *)calloc(n, 4); S.ep_len = (int *)calloc(n, 4);
+  S.event = (uint32_t *)calloc(n, 4); S.time_table = e->tt; S.stats = e->stats;
+  return e;
+}
+extern "C" void emu_destroy(Emu *e) {
+  BrbState &S = e->S;
+  free(S.qpos); free(S.qvel); free(S.xquat); free(S.warm); free(S.last_pitch); free(S.ep_return); free(S.v3);
+  free(S.elapsed); free(S.ep_len); free(S.event); free(e->tt); free(e);
+}
+template <int KIND> static void reset_all(Emu *e, float *obs, const double *replay) {
+  for (long long i = 0; i < e->S.n; i++) {
+    double ur[16];
+    if (replay) memcpy(ur, replay + 16 * i, sizeof ur);
+    else for (int b = 0; b < 4; b++) draw4(e->S.seed, (uint64_t)(e->S.env0 + i), 0u, 1u + b, ur + 4 * b);
+    e->S.event[i] = 0;
+    reset_env<KIND>(e->S, i, ur, obs + 6 * i);
+  }
+}
+extern "C" void emu_reset(Emu *e, float *obs, const double *replay) {
+  switch (e->c.env_kind) {
+    case BRB_ENV01_V1: reset_all<BRB_ENV01_V1>(e, obs, replay); break;
+    case BRB_ENV01_V2: reset_all<BRB_ENV01_V2>(e, obs, replay); break;
+    default: reset_all<BRB_ENV01_V3>(e, obs, replay); break;
+  }
+}
+template <int KIND> static void step_all(Emu *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *trunc,
+                                         float *tobs, float *epr, int32_t *epl, const double *replay) {
+  for (long long i = 0; i < e->S.n; i++) {
+    unsigned stat[6] = {0, 0, 0, 0, 0, 0};
+    step_env<KIND>(e->c, e->S, i, actions, obs, reward, done, trunc, tobs, epr, epl, replay, stat);
+    for (int k = 0; k < 6; k++) e->stats[k] += stat[k];
+    e->stats[BRB_STAT_ENV_STEPS] += 1;
+  }
+}
+extern "C" void emu_step(Emu *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *trunc, float *tobs,
+                         float *epr, int32_t *epl, const double *replay) {
+  switch (e->c.env_kind) {
+    case BRB_ENV01_V1: step_all<BRB_ENV01_V1>(e, actions, obs, reward, done, trunc, tobs, epr, epl, replay); break;
+    case BRB_ENV01_V2: step_all<BRB_ENV01_V2>(e, actions, obs, reward, done, trunc, tobs, epr, epl, replay); break;
+    default: step_all<BRB_ENV01_V3>(e, actions, obs, reward, done, trunc, tobs, epr, epl, replay); break;
+  }
+}
+extern "C" void emu_get_state(Emu *e, double *qpos, double *qvel, double *xquat) {
+  const long long n = e->S.n;
+  for (long long i = 0; i < n; i++) {
+    for (int k = 0; k < 9; k++) qpos[i * 9 + k] = e->S.qpos[k * n + i];
+    for (int k = 0; k < 8; k++) qvel[i * 8 + k] = e->S.qvel[k * n + i];
+    if (xquat) for (int k = 0; k < 4; k++) xquat[i * 4 + k] = e->S.xquat[k * n + i];
+  }
+}
+extern "C" void emu_set_state(Emu *e, const double *qpos, const double *qvel) {
+  const long long n = e->S.n;
+  for (long long i = 0; i < n; i++) {
+    for (int k = 0; k < 9; k++) e->S.qpos[k * n + i] = qpos[i * 9 + k];
+    for (int k = 0; k < 8; k++) { e->S.qvel[k * n + i] = qvel[i * 8 + k]; e->S.warm[k * n + i] = 0.f; }
+    double nn = 0;
+    for (int k = 0; k < 4; k++) nn += qpos[i * 9 + 3 + k] * qpos[i * 9 + 3 + k];
+    nn = 1.0 / sqrt(nn);
+    for (int k = 0; k < 4; k++) e->S.xquat[k * n + i] = qpos[i * 9 + 3 + k] * nn;
+  }
+}
+extern "C" void emu_get_stats(Emu *e, unsigned long long *out) { memcpy(out, e->stats, sizeof e->stats); }
