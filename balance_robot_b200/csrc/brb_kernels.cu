@@ -77,7 +77,7 @@ BRB_D void draw4(uint64_t seed, uint64_t env, uint32_t event, uint32_t block, do
 }
 
 // ---------------------------------------------------------------------------------------------------
-// task-logic helpers (fp64; restate the reference Python, see oracle/brb_ref_env.c for the twin)
+// task-logic helpers (fp64; restate the reference Python, the oracle restates the same logic independently)
 BRB_D double pitch_of(const double q[4]) {  // RobotBaseEnv.py:127-135
   if (q[0] == 0.0) return 0.0;
   double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
@@ -132,7 +132,7 @@ BRB_D void obs_of(double pitch, double pitch_dot, double vl, double vr, double t
 }
 
 // reset_model (env01_v1.py:39-58, env01_v2.py:52-71, env01_v3.py:39-54) + first observation.
-// u[0..15]: slots documented in oracle/brb_ref_env.c.
+// u[0..15]: draw-slot layout: DESIGN.md §4.
 template <int KIND>
 BRB_D void reset_env(const BrbState &S, long long i, const double u[16], float o[6]) {
   const long long N = S.n;

@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""bench.py — env-steps/s of the fused Env01-v2 step (BASELINE.json metric) on N B200s, device-timed.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # the CPU restatement of the reference step (oracle), host cores
+
+One "step" = one VecEnv.step over every env of the shard = 250 physics substeps per env + task logic +
+auto-reset.  Workload at N=1: BASELINE.json configs[1] — Env01-v2, 65,536 envs, random
+actions a ~ U(-1,1)^2 (torch.Generator(device).manual_seed(1234)), Philox noise, auto-reset on.  N>1: the same
+shard on every rank (weak scaling), Philox streams keyed by global env id, no collective in the step.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract: roofline (FP32-pipe bound: the schema's
+"hbm|tensor" does not apply to this path), cpu_baseline, e2e, clocks, gpu_launches.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import pathlib
+import subprocess
+import sys
+import time
+
+ROOT = pathlib.Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = "env-steps/sec (Env01-v2, device-timed)"
+UNIT = "env-steps/s"
+ENV_ID = "Env01-v2"
+FLOP_PER_SUBSTEP_CONTACT = 3700.0   # 4 contacts, one solver pass, nv = 8
+FLOP_PER_SUBSTEP_AIR = 1000.0
+FRAME_SKIP = 250
+ALG_FLOP_PER_ENV_STEP = FLOP_PER_SUBSTEP_CONTACT * FRAME_SKIP          # 9.25e5 ("9.3e5" in SURVEY.md)
+ALG_BYTES_PER_ENV_STEP = 290.0
+NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--envs-per-gpu", type=int, default=65536)
+    ap.add_argument("--env", default=ENV_ID)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cpu-threads", type=int, default=0, help="threads for the CPU legs (0 = all cores)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(args, world):
+    return {"workload": f"{args.env} random-action rollout, {args.envs_per_gpu} envs per GPU x {world} GPU(s), "
+                        "250 substeps/step (h=2e-5, implicitfast), auto-reset, Philox noise",
+            "env": args.env, "envs_per_gpu": args.envs_per_gpu, "n_envs": args.envs_per_gpu * world,
+            "frame_skip": FRAME_SKIP, "actions": "U(-1,1)^2, torch.Generator(cuda).manual_seed(1234)",
+            "cache": "L2 flushed (256 MiB write) before every timed step", "sharding": f"env-dp{world}"}
+
+
+# ------------------------------------------------------------------------------------------------ CPU legs (oracle)
+def cpu_leg(args, steps, warmup, threads):
+    """Times the fp64 oracle (CPU restatement of the reference step; MuJoCo itself is not installable here)
+    over 64 envs per thread with the same action distribution and replayed Philox draws."""
+    import numpy as np
+    from balance_robot_b200 import mjcf, registry
+    from oracle import ref
+    spec = registry.spec(args.env)
+    n = 64 * threads
+    rv = ref.RefVecEnv(mjcf.parse(spec.scene), args.env, n, spec.max_episode_steps, nthreads=threads)
+    _, ur = ref.philox_draws(args.seed, 0, n, 0)
+    rv.reset(ur)
+    rng = np.random.default_rng(1234)
+    draws = [ref.philox_draws(args.seed, 0, n, k + 1) for k in range(warmup + steps)]
+    acts = rng.uniform(-1, 1, (warmup + steps, n, 2)).astype(np.float32)
+    for k in range(warmup):
+        rv.step(acts[k], *draws[k])
+    t0 = time.perf_counter()
+    for k in range(warmup, warmup + steps):
+        rv.step(acts[k], *draws[k])
+    dt = time.perf_counter() - t0
+    rv.close()
+    return n * steps / dt, dt, n
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    threads = args.cpu_threads or (os.cpu_count() or 1)
+    value, dt, n = cpu_leg(args, args.steps, args.warmup, threads)
+    sample = f"{n} envs (64 per thread) x {args.steps} steps after {args.warmup} warm-up, same action distribution, replayed Philox draws"
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "config": workload_config(args, world), "impl": "reference",
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "note": "reference arm = fp64 C restatement of the reference step (oracle/); mujoco/gymnasium/SB3 are not installable offline"}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons, pw = [], [], set(), []
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in out.strip().splitlines():
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1])); pw.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        sm_sorted = sorted(sm)
+        # median over the busier half of the samples (the sampler also sees the idle edges of the region)
+        busy = sm_sorted[len(sm_sorted) // 2:]
+        return {"sm_mhz": busy[len(busy) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_max": max(pw)}
+
+
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import ctypes as C
+    from balance_robot_b200 import make_vec, _cabi
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs_per_gpu
+    env = make_vec(args.env, n, device=dev, seed=args.seed, env_id_offset=rank * n)
+    env.reset()
+    gen = torch.Generator(device=dev).manual_seed(1234 + rank)
+    nact = 16
+    acts = [torch.rand((n, 2), device=dev, generator=gen) * 2 - 1 for _ in range(nact)]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    # FP32-pipe peak probe (roofline denominator, measured in this run)
+    fl, ms = C.c_double(), C.c_double()
+    _cabi.check(_cabi.lib().brb_fp32_peak_flops(local_rank, C.byref(fl), C.byref(ms)), "brb_fp32_peak_flops")
+    fp32_peak = fl.value
+
+    for k in range(args.warmup):
+        env.step(acts[k % nact])
+    torch.cuda.synchronize(dev)
+    stats0 = env.stats()
+    launches0 = env.num_launches()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    wall0 = time.perf_counter()
+    for k in range(args.steps):
+        flush.fill_(k & 0xFF)            # evict L2 (126 MB) between timed steps; not inside the event pair
+        ev[k][0].record()
+        env.step(acts[k % nact])
+        ev[k][1].record()
+    torch.cuda.synchronize(dev)
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop() if sampler else None
+    step_ms = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(step_ms)
+    launches = env.num_launches() - launches0
+    stats1 = env.stats()
+    if dist is not None:
+        t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = n * world * args.steps / (total_ms * 1e-3)
+
+    # ---- e2e: the SB3 contract through the C-ABI host call (numpy in / numpy out, pinned staging, copies timed)
+    e2e = None
+    if not args.no_e2e:
+        import numpy as np
+        env_h = make_vec(args.env, n, device=dev, seed=args.seed + 1, env_id_offset=rank * n, output="numpy")
+        env_h.reset()
+        rng = np.random.default_rng(99 + rank)
+        acts_h = [rng.uniform(-1, 1, (n, 2)).astype(np.float32) for _ in range(4)]
+        e2e_steps = max(10, min(args.steps, 50))
+        for k in range(3):
+            env_h.step(acts_h[k % 4])
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        for k in range(e2e_steps):
+            obs_h, rew_h, done_h, infos_h = env_h.step(acts_h[k % 4])
+        torch.cuda.synchronize(dev)
+        dt = time.perf_counter() - t0
+        if dist is not None:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {"value": n * world * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * 2 * 4,
+               "d2h_bytes_per_step": n * (6 * 4 + 4 + 1 + 1 + 6 * 4 + 4 + 4), "steps": e2e_steps,
+               "path": "BalanceVecEnv(output='numpy').step -> brb_env_step_host (numpy actions in, numpy obs/reward/done + SB3 infos out)"}
+        env_h.close()
+
+    if rank != 0:
+        env.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    sub = stats1["substeps"] - stats0["substeps"]
+    csub = stats1["contact_substeps"] - stats0["contact_substeps"]
+    active = csub / max(1, sub)
+    kernel_ms = total_ms / args.steps
+    # roofline of the dominant (only) kernel, per launch = one shard step
+    alg_flop_launch = ALG_FLOP_PER_ENV_STEP * n
+    achieved = alg_flop_launch / (kernel_ms * 1e-3) / 1e12
+    occ_flop = FRAME_SKIP * (FLOP_PER_SUBSTEP_AIR + (FLOP_PER_SUBSTEP_CONTACT - FLOP_PER_SUBSTEP_AIR) * active) * n
+    try:
+        peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
+    except Exception:
+        peaks = {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
+                "frac": achieved / (fp32_peak / 1e12),
+                "traffic": None,
+                "peak_source": "FFMA probe kernel measured in this run (brb_fp32_peak_flops); MEASURED_PEAKS.json has no FP32 entry; "
+                               f"nominal {NOMINAL_FP32_TFLOPS:.1f}",
+                "algorithmic_flop_per_env_step": ALG_FLOP_PER_ENV_STEP,
+                "contact_active_fraction": active,
+                "achieved_contact_weighted": occ_flop / (kernel_ms * 1e-3) / 1e12,
+                "frac_contact_weighted": occ_flop / (kernel_ms * 1e-3) / fp32_peak,
+                "hbm": {"achieved_gbs": ALG_BYTES_PER_ENV_STEP * n / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
+                "kernel": "brb_step_kernel<Env01_v2>", "kernel_ms": kernel_ms}
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world >= 1:
+        threads = args.cpu_threads or (os.cpu_count() or 1)
+        v, dt, ncpu = cpu_leg(args, 120, 10, threads)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{ncpu} envs (64 per thread) x 120 steps after 10 warm-up ({dt:.1f} s), fp64 oracle, replayed Philox draws"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "wall_s": wall,
+            "solver": {"nonconverged_substeps": stats1["nonconverged"] - stats0["nonconverged"],
+                       "unsupported_pose_steps": stats1["unsupported"] - stats0["unsupported"],
+                       "solves_per_contact_substep": (stats1["solves"] - stats0["solves"]) / max(1, csub),
+                       "episodes": stats1["episodes"] - stats0["episodes"]}}
+    print(json.dumps(line), flush=True)
+    env.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
+               "--master-addr", "127.0.0.1", "--master-port", str(29500 + os.getpid() % 1000)] + sys.argv
+        raise SystemExit(subprocess.call(cmd))
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()
