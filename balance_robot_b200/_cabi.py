@@ -14,13 +14,14 @@ from .model import BrbModelConsts
 
 CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "libbrb_cuda.so"
+_EXPERIMENT_LIB = "BRB_EXPERIMENT_LIB"   # kernel-tuning experiments only (scripts/): alternative build of the SAME sources
 SOURCES = ("brb_kernels.cu", "brb_cabi.cu")
-HEADERS = (CSRC / "brb_internal.h", CSRC.parent.parent / "include" / "brb.h")
+HEADERS = (CSRC / "brb_internal.h", CSRC / "brb_chol8.inc", CSRC.parent.parent / "include" / "brb.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 NSTATS = 8
-STAT_NAMES = ("substeps", "contact_substeps", "solves", "nonconverged", "unsupported", "episodes", "env_steps", "_")
+STAT_NAMES = ("substeps", "contact_substeps", "solves", "nonconverged", "unsupported", "episodes", "env_steps", "contact_slots")
 
 EXPORTS = (
     "brb_version", "brb_strerror", "brb_model_create", "brb_model_destroy", "brb_env_create", "brb_env_destroy",
@@ -57,10 +58,12 @@ def lib() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists():
+    import os
+    path = pathlib.Path(os.environ.get(_EXPERIMENT_LIB, LIB_PATH))
+    if not path.exists():
         raise BrbError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(there is no CPU fallback for the env step)")
-    L = C.CDLL(str(LIB_PATH))
+    L = C.CDLL(str(path))
     vp, i64, u64 = C.c_void_p, C.c_int64, C.c_uint64
     L.brb_version.restype = C.c_int
     L.brb_strerror.restype = C.c_char_p

@@ -3,7 +3,12 @@
 #define BRB_INTERNAL_H
 #include <stdint.h>
 
-#define BRB_BLOCK 128   // threads per CTA of the step kernel (one env per thread)
+#ifndef BRB_BLOCK
+#define BRB_BLOCK 64    // threads per CTA of the step kernel (one env per thread)
+#endif
+#ifndef BRB_MINBLOCKS
+#define BRB_MINBLOCKS 6 // __launch_bounds__ min resident CTAs per SM (register cap = 65536 / (BRB_BLOCK * BRB_MINBLOCKS))
+#endif
 #define BRB_MAXIT 8     // cap on active-set (Newton) iterations per substep
 
 // Struct-of-arrays env state in HBM: column k of a [K][N] array lives at base + k*N, so a warp's 32
@@ -24,5 +29,14 @@ struct BrbState {
   uint32_t *event;        // [N]     Philox event counter (0 = reset_all, k = k-th step call)
   const double *time_table;  // [max_episode_steps + 2] fp64 data.time after k env steps
   unsigned long long *stats; // [BRB_NSTATS]
+};
+
+// Visit order of the step kernel (double-buffered): in = order for this launch (NULL = identity), out = order the
+// launch builds for the next one (airborne robots packed from the front, grounded from the back).
+struct BrbPerm {
+  const int *in;
+  int *out;
+  unsigned *cnt_out;   // [2] slot counters for `out`, zero on entry
+  unsigned *cnt_zero;  // [2] the other buffer's counters, cleared for the next launch
 };
 #endif

@@ -26,6 +26,7 @@
 #ifdef BRB_HOST_EMU
 #include "emu_shim.h"
 #define BRB_D static inline
+#define __popc(x) __builtin_popcount(x)
 #else
 #include <cuda_runtime.h>
 #define BRB_D __device__ __forceinline__
@@ -180,284 +181,299 @@ BRB_D void reset_env(const BrbState &S, long long i, const double u[16], float o
 }
 
 // ---------------------------------------------------------------------------------------------------
-// packed lower-triangular index
-#define LT(i, j) ((i) * ((i) + 1) / 2 + (j))
+// Physics.  Everything below works on registers of one thread (= one robot).  Contact slots are addressed
+// with compile-time indices only (template<int CI>), so the 8x8 system and the contact records stay in
+// registers (a run-time contact index sends H[] to local memory — measured in profiles/r1a).
+#define LT(i, j) ((i) * ((i) + 1) / 2 + (j))   // packed lower-triangular index
 
-struct Contact { float rx, ry, rz, y0, y1, y2; };
-
-// One physics substep.  All arguments are registers of the calling thread.
-struct Sub {
+struct Phys {
+  // ---- state carried across substeps
   KF p[3], q[4], th[2], v[3], w[3], s[2];   // world pos, quat (w,x,y,z), wheel angles, world lin vel, body ang vel, wheel speeds
-  float a[8];                               // body-frame solver acceleration (warm start for the next substep)
+  float a[8];                               // chassis-frame solver acceleration (warm start for the next substep)
   float uhi[2], ulo[2];                     // clamped ctrl targets, split hi/lo
-  unsigned n_contact, n_solve, n_nonconv;
+  // ---- working set of the current substep (setup() .. finalize())
+  float Xb[3], Yb[3], Zb[3];                // rows of R = world x/y/z axes in the chassis frame (contact frame: n=Zb, t1=Yb, t2=-Xb)
+  float f[8];                               // smooth generalized force in the chassis frame
+  float cr[4][3], cy[4][3];                 // contact point (chassis frame) and yhat = B*vel + (Kimp*dist, 0, 0)
+  unsigned valid;                           // bit ci: contact slot ci (2*wheel + rim end) is in contact
+  bool clampL, clampR;                      // servo sits on its forcerange (A.9)
+  unsigned n_contact, n_solve, n_nonconv, n_slots;
 };
 
-template <int MAXIT>
-BRB_D void substep(const BrbModelConsts &c, Sub &st) {
-  const float qw = st.q[0].s, qx = st.q[1].s, qy = st.q[2].s, qz = st.q[3].s;
-  // rows of R = world axes expressed in the chassis frame
-  const float xx = qx * qx, yy = qy * qy, zz = qz * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz, wx = qw * qx, wy = qw * qy, wz = qw * qz;
-  const float Xb0 = 1.f - 2.f * (yy + zz), Xb1 = 2.f * (xy - wz), Xb2 = 2.f * (xz + wy);
-  const float Yb0 = 2.f * (xy + wz), Yb1 = 1.f - 2.f * (xx + zz), Yb2 = 2.f * (yz - wx);
-  const float Zb0 = 2.f * (xz - wy), Zb1 = 2.f * (yz + wx), Zb2 = 1.f - 2.f * (xx + yy);
-  const float w0 = st.w[0].s, w1 = st.w[1].s, w2 = st.w[2].s, sL = st.s[0].s, sR = st.s[1].s;
+// ---- A.3 steps 2-7: kinematics, smooth forces, collision, reference accelerations
+template <int CI>
+BRB_D void contact_setup(const BrbModelConsts &c, Phys &P, float d0, float anx, float sa, float vy, float vz, float u0, float u1,
+                         float u2) {
+  constexpr int k = CI >> 1, e = CI & 1;
+  const float sg = k ? 1.f : -1.f;
+  const float dist = e ? d0 + c.hl * anx : d0 - c.hl * anx;
+  if (dist < 0.f) {
+    P.valid |= 1u << CI;
+    const float hd = 0.5f * dist;
+    const float rx = sg * c.ox + (e ? -sa : sa) * c.hl - P.Zb[0] * hd;
+    const float ry = vy - P.Zb[1] * hd;
+    const float rz = c.oz + vz - P.Zb[2] * hd;
+    const float w0 = P.w[0].s, w1 = P.w[1].s, w2 = P.w[2].s, sk = P.s[k].s;
+    // material-point velocity: u + w x r + s_k * sg * (0, -(rz-oz), ry)
+    const float px = u0 + w1 * rz - w2 * ry;
+    const float py = u1 + w2 * rx - w0 * rz - sk * sg * (rz - c.oz);
+    const float pz = u2 + w0 * ry - w1 * rx + sk * sg * ry;
+    P.cr[CI][0] = rx; P.cr[CI][1] = ry; P.cr[CI][2] = rz;
+    P.cy[CI][0] = c.Bdamp * (P.Zb[0] * px + P.Zb[1] * py + P.Zb[2] * pz) + c.Kimp * dist;
+    P.cy[CI][1] = c.Bdamp * (P.Yb[0] * px + P.Yb[1] * py + P.Yb[2] * pz);
+    P.cy[CI][2] = -c.Bdamp * (P.Xb[0] * px + P.Xb[1] * py + P.Xb[2] * pz);
+  }
+}
 
-  // ---- smooth forces in the chassis frame (A.3 steps 4-6) ----
-  float f[8];
+BRB_D void phys_setup(const BrbModelConsts &c, Phys &P) {
+  const float qw = P.q[0].s, qx = P.q[1].s, qy = P.q[2].s, qz = P.q[3].s;
+  const float xx = qx * qx, yy = qy * qy, zz = qz * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz, wx = qw * qx, wy = qw * qy, wz = qw * qz;
+  P.Xb[0] = 1.f - 2.f * (yy + zz); P.Xb[1] = 2.f * (xy - wz); P.Xb[2] = 2.f * (xz + wy);
+  P.Yb[0] = 2.f * (xy + wz); P.Yb[1] = 1.f - 2.f * (xx + zz); P.Yb[2] = 2.f * (yz - wx);
+  P.Zb[0] = 2.f * (xz - wy); P.Zb[1] = 2.f * (yz + wx); P.Zb[2] = 1.f - 2.f * (xx + yy);
+  const float w0 = P.w[0].s, w1 = P.w[1].s, w2 = P.w[2].s, sL = P.s[0].s, sR = P.s[1].s;
   {
     const float mg = c.mass * c.grav, gm = c.grav * c.mcz;
-    f[0] = -c.mcz * (w0 * w2) - mg * Zb0;
-    f[1] = -c.mcz * (w1 * w2) - mg * Zb1;
-    f[2] = c.mcz * (w0 * w0 + w1 * w1) - mg * Zb2;
+    P.f[0] = -c.mcz * (w0 * w2) - mg * P.Zb[0];
+    P.f[1] = -c.mcz * (w1 * w2) - mg * P.Zb[1];
+    P.f[2] = c.mcz * (w0 * w0 + w1 * w1) - mg * P.Zb[2];
     const float Lx = c.Ixx * w0 + c.Ia * (sR - sL), Ly = c.Iyy * w1, Lz = c.Izz * w2;
-    f[3] = -(w1 * Lz - w2 * Ly) + gm * Zb1;
-    f[4] = -(w2 * Lx - w0 * Lz) - gm * Zb0;
-    f[5] = -(w0 * Ly - w1 * Lx);
-  }
-  bool clampL, clampR;
-  {
+    P.f[3] = -(w1 * Lz - w2 * Ly) + gm * P.Zb[1];
+    P.f[4] = -(w2 * Lx - w0 * Lz) - gm * P.Zb[0];
+    P.f[5] = -(w0 * Ly - w1 * Lx);
     // servo: force = clip(kv (u - s), forcerange); u - s evaluated with the hi/lo halves (Q7)
-    float dL = (st.uhi[0] - sL) + (st.ulo[0] + st.s[0].c), dR = (st.uhi[1] - sR) + (st.ulo[1] + st.s[1].c);
+    const float dL = (P.uhi[0] - sL) + (P.ulo[0] + P.s[0].c), dR = (P.uhi[1] - sR) + (P.ulo[1] + P.s[1].c);
     float tL = c.kv * dL, tR = c.kv * dR;
-    clampL = (tL <= c.frc_lo) || (tL >= c.frc_hi);
-    clampR = (tR <= c.frc_lo) || (tR >= c.frc_hi);
+    P.clampL = (tL <= c.frc_lo) || (tL >= c.frc_hi);
+    P.clampR = (tR <= c.frc_lo) || (tR >= c.frc_hi);
     tL = fminf(c.frc_hi, fmaxf(c.frc_lo, tL));
     tR = fminf(c.frc_hi, fmaxf(c.frc_lo, tR));
-    f[6] = tL - c.damping * sL;
-    f[7] = tR - c.damping * sR;
+    P.f[6] = tL - c.damping * sL;
+    P.f[7] = tR - c.damping * sR;
   }
+  // plane-cylinder collision in the chassis frame (A.6): both rim ends of both wheels
+  P.valid = 0;
+  const float rho2 = P.Zb[1] * P.Zb[1] + P.Zb[2] * P.Zb[2];
+  const float irho = rsqrtf(fmaxf(rho2, 1e-30f));
+  const float rho = rho2 * irho;
+  // oz*nz - rad*rho without cancellation when upright: (oz-rad) nz + rad (nz - rho), nz - rho = -ny^2/(nz+rho)
+  const float diff = (P.Zb[2] > 0.f) ? -(P.Zb[1] * P.Zb[1]) / (P.Zb[2] + rho) : (P.Zb[2] - rho);
+  const float hgt = ((P.p[2].s - c.zfloor) - P.p[2].c) - c.zfloor_lo;
+  const float common = hgt + (c.oz - c.rad) * P.Zb[2] + c.rad * diff;
+  const float anx = fabsf(P.Zb[0]);
+  const float dmin = common - c.ox * anx - c.hl * anx;          // lowest rim point of either wheel
+  if (dmin < 0.f) {
+    const float vy = -c.rad * P.Zb[1] * irho, vz = -c.rad * P.Zb[2] * irho;
+    const float sa = (P.Zb[0] > 0.f) ? -1.f : 1.f;
+    const float u0 = P.v[0].s * P.Xb[0] + P.v[1].s * P.Yb[0] + P.v[2].s * P.Zb[0];   // chassis-frame linear velocity
+    const float u1 = P.v[0].s * P.Xb[1] + P.v[1].s * P.Yb[1] + P.v[2].s * P.Zb[1];
+    const float u2 = P.v[0].s * P.Xb[2] + P.v[1].s * P.Yb[2] + P.v[2].s * P.Zb[2];
+    const float dL0 = common - c.ox * P.Zb[0], dR0 = common + c.ox * P.Zb[0];
+    contact_setup<0>(c, P, dL0, anx, sa, vy, vz, u0, u1, u2);
+    contact_setup<1>(c, P, dL0, anx, sa, vy, vz, u0, u1, u2);
+    contact_setup<2>(c, P, dR0, anx, sa, vy, vz, u0, u1, u2);
+    contact_setup<3>(c, P, dR0, anx, sa, vy, vz, u0, u1, u2);
+  }
+  if (P.valid) { P.n_contact++; P.n_slots += __popc(P.valid); }
+}
 
-  // ---- plane-cylinder collision in the chassis frame (A.6) ----
-  Contact ct[4];
-  unsigned valid = 0;
+// ---- active set at acceleration a: z_c = B (P_c a) + yhat_c, pyramid rows E_r . z_c < 0 (A.7, A.8).
+// Rows within `eps` of the switching surface keep their previous state (`prev`): either choice gives the same
+// force to O(D*eps) ~ 2e-5 N, and without the hysteresis fp32 noise can flip such a row back and forth forever.
+template <int CI>
+BRB_D unsigned contact_bits(const BrbModelConsts &c, const Phys &P, unsigned prev) {
+  if (!(P.valid & (1u << CI))) return 0u;
+  constexpr int k = CI >> 1;
+  const float sg = k ? 1.f : -1.f;
+  const float ak = P.a[6 + k];
+  const float rx = P.cr[CI][0], ry = P.cr[CI][1], rz = P.cr[CI][2];
+  const float px = P.a[0] + P.a[4] * rz - P.a[5] * ry;
+  const float py = P.a[1] + P.a[5] * rx - P.a[3] * rz - ak * sg * (rz - c.oz);
+  const float pz = P.a[2] + P.a[3] * ry - P.a[4] * rx + ak * sg * ry;
+  const float z0 = P.Zb[0] * px + P.Zb[1] * py + P.Zb[2] * pz + P.cy[CI][0];
+  const float z1 = c.mu * (P.Yb[0] * px + P.Yb[1] * py + P.Yb[2] * pz + P.cy[CI][1]);
+  const float z2 = c.mu * (P.cy[CI][2] - (P.Xb[0] * px + P.Xb[1] * py + P.Xb[2] * pz));
+  const float eps = 2e-4f;
+  const unsigned pb = prev >> (4 * CI);
+  const float e0 = (pb & 1u) ? eps : -eps, e1 = (pb & 2u) ? eps : -eps, e2 = (pb & 4u) ? eps : -eps, e3 = (pb & 8u) ? eps : -eps;
+  return ((unsigned)(z0 + z1 < e0) | ((unsigned)(z0 - z1 < e1) << 1) | ((unsigned)(z0 + z2 < e2) << 2) | ((unsigned)(z0 - z2 < e3) << 3)) << (4 * CI);
+}
+
+BRB_D unsigned phys_active_set(const BrbModelConsts &c, const Phys &P, unsigned prev) {
+  return contact_bits<0>(c, P, prev) | contact_bits<1>(c, P, prev) | contact_bits<2>(c, P, prev) | contact_bits<3>(c, P, prev);
+}
+
+// ---- H += P_c' S_c P_c, r -= P_c' B' W_c yhat_c for one contact, S_c = B' W_c B
+template <int CI>
+BRB_D void contact_assemble(const BrbModelConsts &c, const Phys &P, unsigned bits, float (&H)[36], float (&r)[8]) {
+  const unsigned b = (bits >> (4 * CI)) & 15u;
+  if ((P.valid & (1u << CI)) && b) {
+    constexpr int kw = 6 + (CI >> 1);
+    const float sg = (CI >> 1) ? 1.f : -1.f;
+    const float b0 = (float)(b & 1u), b1 = (float)((b >> 1) & 1u), b2 = (float)((b >> 2) & 1u), b3 = (float)((b >> 3) & 1u);
+    const float Dm = c.D * c.mu, Dmm = Dm * c.mu;
+    const float W00 = c.D * (b0 + b1 + b2 + b3), W01 = Dm * (b0 - b1), W02 = Dm * (b2 - b3);
+    const float W11 = Dmm * (b0 + b1), W22 = Dmm * (b2 + b3);
+    const float *X = P.Xb, *Y = P.Yb, *Z = P.Zb;
+    // rows of W B with B = [Zb; Yb; -Xb]
+    const float g00 = W00 * Z[0] + W01 * Y[0] - W02 * X[0], g01 = W00 * Z[1] + W01 * Y[1] - W02 * X[1], g02 = W00 * Z[2] + W01 * Y[2] - W02 * X[2];
+    const float g10 = W01 * Z[0] + W11 * Y[0], g11 = W01 * Z[1] + W11 * Y[1], g12 = W01 * Z[2] + W11 * Y[2];
+    const float g20 = W02 * Z[0] - W22 * X[0], g21 = W02 * Z[1] - W22 * X[1], g22 = W02 * Z[2] - W22 * X[2];
+    const float S00 = Z[0] * g00 + Y[0] * g10 - X[0] * g20, S01 = Z[0] * g01 + Y[0] * g11 - X[0] * g21, S02 = Z[0] * g02 + Y[0] * g12 - X[0] * g22;
+    const float S11 = Z[1] * g01 + Y[1] * g11 - X[1] * g21, S12 = Z[1] * g02 + Y[1] * g12 - X[1] * g22;
+    const float S22 = Z[2] * g02 + Y[2] * g12 - X[2] * g22;
+    const float rx = P.cr[CI][0], ry = P.cr[CI][1], rz = P.cr[CI][2];
+    const float wy_ = -sg * (rz - c.oz), wz_ = sg * ry;
+    // columns of P: e_x e_y e_z | cx=(0,-rz,ry) cy=(rz,0,-rx) cz=(-ry,rx,0) | w=(0,wy_,wz_);  T_j = S p_j
+    const float T3x = -rz * S01 + ry * S02, T3y = -rz * S11 + ry * S12, T3z = -rz * S12 + ry * S22;
+    const float T4x = rz * S00 - rx * S02, T4y = rz * S01 - rx * S12, T4z = rz * S02 - rx * S22;
+    const float T5x = -ry * S00 + rx * S01, T5y = -ry * S01 + rx * S11, T5z = -ry * S02 + rx * S12;
+    const float Twx = wy_ * S01 + wz_ * S02, Twy = wy_ * S11 + wz_ * S12, Twz = wy_ * S12 + wz_ * S22;
+    H[LT(0, 0)] += S00; H[LT(1, 0)] += S01; H[LT(2, 0)] += S02; H[LT(1, 1)] += S11; H[LT(2, 1)] += S12; H[LT(2, 2)] += S22;
+    H[LT(3, 0)] += T3x; H[LT(3, 1)] += T3y; H[LT(3, 2)] += T3z;
+    H[LT(4, 0)] += T4x; H[LT(4, 1)] += T4y; H[LT(4, 2)] += T4z;
+    H[LT(5, 0)] += T5x; H[LT(5, 1)] += T5y; H[LT(5, 2)] += T5z;
+    H[LT(3, 3)] += -rz * T3y + ry * T3z;
+    H[LT(4, 3)] += rz * T3x - rx * T3z;
+    H[LT(5, 3)] += -ry * T3x + rx * T3y;
+    H[LT(4, 4)] += rz * T4x - rx * T4z;
+    H[LT(5, 4)] += -ry * T4x + rx * T4y;
+    H[LT(5, 5)] += -ry * T5x + rx * T5y;
+    H[LT(kw, 0)] += Twx; H[LT(kw, 1)] += Twy; H[LT(kw, 2)] += Twz;
+    H[LT(kw, 3)] += -rz * Twy + ry * Twz;
+    H[LT(kw, 4)] += rz * Twx - rx * Twz;
+    H[LT(kw, 5)] += -ry * Twx + rx * Twy;
+    H[LT(kw, kw)] += wy_ * Twy + wz_ * Twz;
+    // rhs: g = -B' (W yhat)
+    const float y0 = P.cy[CI][0], y1 = P.cy[CI][1], y2 = P.cy[CI][2];
+    const float t0 = W00 * y0 + W01 * y1 + W02 * y2, t1 = W01 * y0 + W11 * y1, t2 = W02 * y0 + W22 * y2;
+    const float gx = -(t0 * Z[0] + t1 * Y[0] - t2 * X[0]), gy = -(t0 * Z[1] + t1 * Y[1] - t2 * X[1]), gz = -(t0 * Z[2] + t1 * Y[2] - t2 * X[2]);
+    r[0] += gx; r[1] += gy; r[2] += gz;
+    r[3] += -rz * gy + ry * gz;
+    r[4] += rz * gx - rx * gz;
+    r[5] += -ry * gx + rx * gy;
+    r[kw] += wy_ * gy + wz_ * gz;
+  }
+}
+
+// ---- one Newton step on the active set `bits`: (M_b + sum P'SP) a = f - sum P'B'W yhat   (A.8; exact for a fixed set)
+BRB_D void phys_solve(const BrbModelConsts &c, Phys &P, unsigned bits) {
+  float H[36], r[8];
+#pragma unroll
+  for (int k = 0; k < 36; k++) H[k] = 0.f;
+  H[LT(0, 0)] = c.mass; H[LT(1, 1)] = c.mass; H[LT(2, 2)] = c.mass;
+  H[LT(4, 0)] = c.mcz; H[LT(3, 1)] = -c.mcz;
+  H[LT(3, 3)] = c.Ixx; H[LT(4, 4)] = c.Iyy; H[LT(5, 5)] = c.Izz;
+  H[LT(6, 3)] = -c.Ia; H[LT(7, 3)] = c.Ia; H[LT(6, 6)] = c.Ia; H[LT(7, 7)] = c.Ia;
+#pragma unroll
+  for (int k = 0; k < 8; k++) r[k] = P.f[k];
+  contact_assemble<0>(c, P, bits, H, r);
+  contact_assemble<1>(c, P, bits, H, r);
+  contact_assemble<2>(c, P, bits, H, r);
+  contact_assemble<3>(c, P, bits, H, r);
+  // Cholesky H = L L' and the two triangular solves, straight-line (generated: gen_chol8.py)
+#include "brb_chol8.inc"
+#pragma unroll
+  for (int k = 0; k < 8; k++) P.a[k] = r[k];
+  P.n_solve++;
+}
+
+// ---- free flight: a = M_b^-1 f
+BRB_D void phys_free_accel(const BrbModelConsts &c, Phys &P) {
+  const float *f = P.f;
+  P.a[0] = c.minv_xy[0] * f[0] + c.minv_xy[1] * f[4];
+  P.a[4] = c.minv_xy[1] * f[0] + c.minv_xy[2] * f[4];
+  P.a[2] = c.minv_uz * f[2];
+  P.a[5] = c.minv_wz * f[5];
+  P.a[1] = c.minv_blk[0] * f[1] + c.minv_blk[1] * f[3] + c.minv_blk[2] * f[6] + c.minv_blk[3] * f[7];
+  P.a[3] = c.minv_blk[1] * f[1] + c.minv_blk[4] * f[3] + c.minv_blk[5] * f[6] + c.minv_blk[6] * f[7];
+  P.a[6] = c.minv_blk[2] * f[1] + c.minv_blk[5] * f[3] + c.minv_blk[7] * f[6] + c.minv_blk[8] * f[7];
+  P.a[7] = c.minv_blk[3] * f[1] + c.minv_blk[6] * f[3] + c.minv_blk[8] * f[6] + c.minv_blk[9] * f[7];
+}
+
+// ---- A.9 + A.10: implicitfast velocity update, then positions with the NEW velocities.  P.a keeps the
+// solver's acceleration (MuJoCo's qacc / qacc_warmstart), the implicit correction is applied to a copy.
+BRB_D void phys_finalize(const BrbModelConsts &c, Phys &P) {
+  float a1 = P.a[1], a3 = P.a[3], a6 = P.a[6], a7 = P.a[7];
   {
-    const float rho2 = Zb1 * Zb1 + Zb2 * Zb2;
-    const float irho = rsqrtf(fmaxf(rho2, 1e-30f));
-    const float rho = rho2 * irho;
-    const float vy = -c.rad * Zb1 * irho, vz = -c.rad * Zb2 * irho;
-    // oz*nz - rad*rho without cancellation when upright: (oz-rad) nz + rad (nz - rho), nz - rho = -ny^2/(nz+rho)
-    const float diff = (Zb2 > 0.f) ? -(Zb1 * Zb1) / (Zb2 + rho) : (Zb2 - rho);
-    const float hgt = ((st.p[2].s - c.zfloor) - st.p[2].c) - c.zfloor_lo;
-    const float common = hgt + (c.oz - c.rad) * Zb2 + c.rad * diff;
-    const float anx = fabsf(Zb0);
-    const float sa = (Zb0 > 0.f) ? -1.f : 1.f;
-    const float u0 = st.v[0].s * Xb0 + st.v[1].s * Yb0 + st.v[2].s * Zb0;   // chassis-frame linear velocity
-    const float u1 = st.v[0].s * Xb1 + st.v[1].s * Yb1 + st.v[2].s * Zb1;
-    const float u2 = st.v[0].s * Xb2 + st.v[1].s * Yb2 + st.v[2].s * Zb2;
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-      const float sg = k ? 1.f : -1.f;
-      const float d0 = common + sg * c.ox * Zb0;
-      const float sk = k ? sR : sL;
-#pragma unroll
-      for (int e = 0; e < 2; e++) {
-        const float dist = e ? d0 + c.hl * anx : d0 - c.hl * anx;
-        if (dist < 0.f) {
-          const int ci = 2 * k + e;
-          valid |= 1u << ci;
-          const float hd = 0.5f * dist;
-          const float rx = sg * c.ox + (e ? -sa : sa) * c.hl - Zb0 * hd;
-          const float ry = vy - Zb1 * hd;
-          const float rz = c.oz + vz - Zb2 * hd;
-          // material-point velocity: u + w x r + s_k * sg * (0, -(rz-oz), ry)
-          const float wy_ = -sg * (rz - c.oz), wz_ = sg * ry;
-          const float px = u0 + w1 * rz - w2 * ry;
-          const float py = u1 + w2 * rx - w0 * rz + sk * wy_;
-          const float pz = u2 + w0 * ry - w1 * rx + sk * wz_;
-          ct[ci].rx = rx; ct[ci].ry = ry; ct[ci].rz = rz;
-          ct[ci].y0 = c.Bdamp * (Zb0 * px + Zb1 * py + Zb2 * pz) + c.Kimp * dist;
-          ct[ci].y1 = c.Bdamp * (Yb0 * px + Yb1 * py + Yb2 * pz);
-          ct[ci].y2 = -c.Bdamp * (Xb0 * px + Xb1 * py + Xb2 * pz);
-        }
-      }
-    }
-  }
-
-  float a[8];
-  if (valid == 0) {
-    // ---- free flight: a = M_b^-1 f ----
-    a[0] = c.minv_xy[0] * f[0] + c.minv_xy[1] * f[4];
-    a[4] = c.minv_xy[1] * f[0] + c.minv_xy[2] * f[4];
-    a[2] = c.minv_uz * f[2];
-    a[5] = c.minv_wz * f[5];
-    a[1] = c.minv_blk[0] * f[1] + c.minv_blk[1] * f[3] + c.minv_blk[2] * f[6] + c.minv_blk[3] * f[7];
-    a[3] = c.minv_blk[1] * f[1] + c.minv_blk[4] * f[3] + c.minv_blk[5] * f[6] + c.minv_blk[6] * f[7];
-    a[6] = c.minv_blk[2] * f[1] + c.minv_blk[5] * f[3] + c.minv_blk[7] * f[6] + c.minv_blk[8] * f[7];
-    a[7] = c.minv_blk[3] * f[1] + c.minv_blk[6] * f[3] + c.minv_blk[8] * f[6] + c.minv_blk[9] * f[7];
-  } else {
-    st.n_contact++;
-#pragma unroll
-    for (int k = 0; k < 8; k++) a[k] = st.a[k];
-    unsigned used = 0xFFFFFFFFu;
-    const float mu = c.mu;
-    int it = 0;
-    for (;; it++) {
-      // ---- active set at the current acceleration: z_c = B (P_c a) + yhat_c, rows E_r . z_c < 0 ----
-      unsigned bits = 0;
-#pragma unroll
-      for (int ci = 0; ci < 4; ci++) {
-        if (valid & (1u << ci)) {
-          const float sg = (ci >> 1) ? 1.f : -1.f;
-          const float ak = a[6 + (ci >> 1)];
-          const float rx = ct[ci].rx, ry = ct[ci].ry, rz = ct[ci].rz;
-          const float px = a[0] + a[4] * rz - a[5] * ry;
-          const float py = a[1] + a[5] * rx - a[3] * rz - ak * sg * (rz - c.oz);
-          const float pz = a[2] + a[3] * ry - a[4] * rx + ak * sg * ry;
-          const float z0 = Zb0 * px + Zb1 * py + Zb2 * pz + ct[ci].y0;
-          const float z1 = mu * (Yb0 * px + Yb1 * py + Yb2 * pz + ct[ci].y1);
-          const float z2 = mu * (ct[ci].y2 - (Xb0 * px + Xb1 * py + Xb2 * pz));
-          bits |= (unsigned)(z0 + z1 < 0.f) << (4 * ci);
-          bits |= (unsigned)(z0 - z1 < 0.f) << (4 * ci + 1);
-          bits |= (unsigned)(z0 + z2 < 0.f) << (4 * ci + 2);
-          bits |= (unsigned)(z0 - z2 < 0.f) << (4 * ci + 3);
-        }
-      }
-      if (bits == used) break;
-      if (it >= MAXIT) { st.n_nonconv++; break; }
-      used = bits;
-      st.n_solve++;
-
-      // ---- H = M_b + sum_c P_c' S_c P_c (packed lower), rhs = f - sum_c P_c' B' W_c yhat_c ----
-      float H[36];
-#pragma unroll
-      for (int k = 0; k < 36; k++) H[k] = 0.f;
-      H[LT(0, 0)] = c.mass; H[LT(1, 1)] = c.mass; H[LT(2, 2)] = c.mass;
-      H[LT(4, 0)] = c.mcz; H[LT(3, 1)] = -c.mcz;
-      H[LT(3, 3)] = c.Ixx; H[LT(4, 4)] = c.Iyy; H[LT(5, 5)] = c.Izz;
-      H[LT(6, 3)] = -c.Ia; H[LT(7, 3)] = c.Ia; H[LT(6, 6)] = c.Ia; H[LT(7, 7)] = c.Ia;
-      float r[8];
-#pragma unroll
-      for (int k = 0; k < 8; k++) r[k] = f[k];
-#pragma unroll
-      for (int ci = 0; ci < 4; ci++) {
-        const unsigned b = (bits >> (4 * ci)) & 15u;
-        if ((valid & (1u << ci)) && b) {
-          const float b0 = (float)(b & 1u), b1 = (float)((b >> 1) & 1u), b2 = (float)((b >> 2) & 1u), b3 = (float)((b >> 3) & 1u);
-          const float Dm = c.D * mu, Dmm = Dm * mu;
-          const float W00 = c.D * (b0 + b1 + b2 + b3), W01 = Dm * (b0 - b1), W02 = Dm * (b2 - b3);
-          const float W11 = Dmm * (b0 + b1), W22 = Dmm * (b2 + b3);
-          // rows of W B with B = [Zb; Yb; -Xb]
-          const float g00 = W00 * Zb0 + W01 * Yb0 - W02 * Xb0, g01 = W00 * Zb1 + W01 * Yb1 - W02 * Xb1, g02 = W00 * Zb2 + W01 * Yb2 - W02 * Xb2;
-          const float g10 = W01 * Zb0 + W11 * Yb0, g11 = W01 * Zb1 + W11 * Yb1, g12 = W01 * Zb2 + W11 * Yb2;
-          const float g20 = W02 * Zb0 - W22 * Xb0, g21 = W02 * Zb1 - W22 * Xb1, g22 = W02 * Zb2 - W22 * Xb2;
-          // S = B' (W B), symmetric
-          const float S00 = Zb0 * g00 + Yb0 * g10 - Xb0 * g20, S01 = Zb0 * g01 + Yb0 * g11 - Xb0 * g21, S02 = Zb0 * g02 + Yb0 * g12 - Xb0 * g22;
-          const float S11 = Zb1 * g01 + Yb1 * g11 - Xb1 * g21, S12 = Zb1 * g02 + Yb1 * g12 - Xb1 * g22;
-          const float S22 = Zb2 * g02 + Yb2 * g12 - Xb2 * g22;
-          const float rx = ct[ci].rx, ry = ct[ci].ry, rz = ct[ci].rz;
-          const float sg = (ci >> 1) ? 1.f : -1.f;
-          const float wy_ = -sg * (rz - c.oz), wz_ = sg * ry;
-          // columns of P: e_x e_y e_z | cx=(0,-rz,ry) cy=(rz,0,-rx) cz=(-ry,rx,0) | w=(0,wy_,wz_)
-          // T_j = S p_j for the angular and wheel columns
-          const float T3x = -rz * S01 + ry * S02, T3y = -rz * S11 + ry * S12, T3z = -rz * S12 + ry * S22;
-          const float T4x = rz * S00 - rx * S02, T4y = rz * S01 - rx * S12, T4z = rz * S02 - rx * S22;
-          const float T5x = -ry * S00 + rx * S01, T5y = -ry * S01 + rx * S11, T5z = -ry * S02 + rx * S12;
-          const float Twx = wy_ * S01 + wz_ * S02, Twy = wy_ * S11 + wz_ * S12, Twz = wy_ * S12 + wz_ * S22;
-          H[LT(0, 0)] += S00; H[LT(1, 0)] += S01; H[LT(2, 0)] += S02; H[LT(1, 1)] += S11; H[LT(2, 1)] += S12; H[LT(2, 2)] += S22;
-          H[LT(3, 0)] += T3x; H[LT(3, 1)] += T3y; H[LT(3, 2)] += T3z;
-          H[LT(4, 0)] += T4x; H[LT(4, 1)] += T4y; H[LT(4, 2)] += T4z;
-          H[LT(5, 0)] += T5x; H[LT(5, 1)] += T5y; H[LT(5, 2)] += T5z;
-          H[LT(3, 3)] += -rz * T3y + ry * T3z;
-          H[LT(4, 3)] += rz * T3x - rx * T3z;
-          H[LT(5, 3)] += -ry * T3x + rx * T3y;
-          H[LT(4, 4)] += rz * T4x - rx * T4z;
-          H[LT(5, 4)] += -ry * T4x + rx * T4y;
-          H[LT(5, 5)] += -ry * T5x + rx * T5y;
-          const int kw = 6 + (ci >> 1);
-          H[LT(kw, 0)] += Twx; H[LT(kw, 1)] += Twy; H[LT(kw, 2)] += Twz;
-          H[LT(kw, 3)] += -rz * Twy + ry * Twz;
-          H[LT(kw, 4)] += rz * Twx - rx * Twz;
-          H[LT(kw, 5)] += -ry * Twx + rx * Twy;
-          H[LT(kw, kw)] += wy_ * Twy + wz_ * Twz;
-          // rhs: g = -B' (W yhat)
-          const float t0 = W00 * ct[ci].y0 + W01 * ct[ci].y1 + W02 * ct[ci].y2;
-          const float t1 = W01 * ct[ci].y0 + W11 * ct[ci].y1;
-          const float t2 = W02 * ct[ci].y0 + W22 * ct[ci].y2;
-          const float gx = -(t0 * Zb0 + t1 * Yb0 - t2 * Xb0), gy = -(t0 * Zb1 + t1 * Yb1 - t2 * Xb1), gz = -(t0 * Zb2 + t1 * Yb2 - t2 * Xb2);
-          r[0] += gx; r[1] += gy; r[2] += gz;
-          r[3] += -rz * gy + ry * gz;
-          r[4] += rz * gx - rx * gz;
-          r[5] += -ry * gx + rx * gy;
-          r[kw] += wy_ * gy + wz_ * gz;
-        }
-      }
-      // ---- Cholesky H = L L' in registers, then solve ----
-      float inv[8];
-#pragma unroll
-      for (int j = 0; j < 8; j++) {
-        float d = H[LT(j, j)];
-#pragma unroll
-        for (int k = 0; k < j; k++) d -= H[LT(j, k)] * H[LT(j, k)];
-        const float id = rsqrtf(d);
-        inv[j] = id;
-#pragma unroll
-        for (int i = j + 1; i < 8; i++) {
-          float t = H[LT(i, j)];
-#pragma unroll
-          for (int k = 0; k < j; k++) t -= H[LT(i, k)] * H[LT(j, k)];
-          H[LT(i, j)] = t * id;
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < 8; i++) {
-        float t = r[i];
-#pragma unroll
-        for (int k = 0; k < i; k++) t -= H[LT(i, k)] * r[k];
-        r[i] = t * inv[i];
-      }
-#pragma unroll
-      for (int i = 7; i >= 0; i--) {
-        float t = r[i];
-#pragma unroll
-        for (int k = i + 1; k < 8; k++) t -= H[LT(k, i)] * r[k];
-        r[i] = t * inv[i];
-      }
-#pragma unroll
-      for (int k = 0; k < 8; k++) a[k] = r[k];
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 8; k++) st.a[k] = a[k];   // qacc_warmstart <- solver qacc (A.3 step 8)
-
-  // ---- implicitfast (A.9): a+ = (M + h Dv)^-1 M a = a - Wm (Cinv + G)^-1 [a6; a7] ----
-  {
+    // a+ = (M + h Dv)^-1 M a = a - Wm (Cinv + G)^-1 [a6; a7]   (Woodbury on the two wheel dofs)
     const bool skip = (c.flags & BRB_FLAG_ACTDERIV_SKIP_CLAMPED) != 0;
-    const float cL = (skip && clampL) ? c.impl_cinv_damp : c.impl_cinv_full;
-    const float cR = (skip && clampR) ? c.impl_cinv_damp : c.impl_cinv_full;
+    const float cL = (skip && P.clampL) ? c.impl_cinv_damp : c.impl_cinv_full;
+    const float cR = (skip && P.clampR) ? c.impl_cinv_damp : c.impl_cinv_full;
     const float k00 = cL + c.impl_G[0], k01 = c.impl_G[1], k11 = cR + c.impl_G[2];
     const float idet = 1.f / (k00 * k11 - k01 * k01);
-    const float y0 = (k11 * a[6] - k01 * a[7]) * idet, y1 = (k00 * a[7] - k01 * a[6]) * idet;
-    a[1] -= c.impl_W[0] * y0 + c.impl_W[1] * y1;
-    a[3] -= c.impl_W[2] * y0 + c.impl_W[3] * y1;
-    a[6] -= c.impl_W[4] * y0 + c.impl_W[5] * y1;
-    a[7] -= c.impl_W[6] * y0 + c.impl_W[7] * y1;
+    const float y0 = (k11 * a6 - k01 * a7) * idet, y1 = (k00 * a7 - k01 * a6) * idet;
+    a1 -= c.impl_W[0] * y0 + c.impl_W[1] * y1;
+    a3 -= c.impl_W[2] * y0 + c.impl_W[3] * y1;
+    a6 -= c.impl_W[4] * y0 + c.impl_W[5] * y1;
+    a7 -= c.impl_W[6] * y0 + c.impl_W[7] * y1;
   }
-
-  // ---- mj_advance (A.10): velocities, then positions with the NEW velocities ----
-  const float h = c.h;
-  kadd(st.v[0], h * (Xb0 * a[0] + Xb1 * a[1] + Xb2 * a[2]));
-  kadd(st.v[1], h * (Yb0 * a[0] + Yb1 * a[1] + Yb2 * a[2]));
-  kadd(st.v[2], h * (Zb0 * a[0] + Zb1 * a[1] + Zb2 * a[2]));
-  kadd(st.w[0], h * a[3]); kadd(st.w[1], h * a[4]); kadd(st.w[2], h * a[5]);
-  kadd(st.s[0], h * a[6]); kadd(st.s[1], h * a[7]);
-  kadd(st.p[0], h * st.v[0].s - h * st.v[0].c);
-  kadd(st.p[1], h * st.v[1].s - h * st.v[1].c);
-  kadd(st.p[2], h * st.v[2].s - h * st.v[2].c);
-  kadd(st.th[0], h * st.s[0].s); kadd(st.th[1], h * st.s[1].s);
+  const float h = c.h, a0 = P.a[0], a2 = P.a[2];
+  kadd(P.v[0], h * (P.Xb[0] * a0 + P.Xb[1] * a1 + P.Xb[2] * a2));
+  kadd(P.v[1], h * (P.Yb[0] * a0 + P.Yb[1] * a1 + P.Yb[2] * a2));
+  kadd(P.v[2], h * (P.Zb[0] * a0 + P.Zb[1] * a1 + P.Zb[2] * a2));
+  kadd(P.w[0], h * a3); kadd(P.w[1], h * P.a[4]); kadd(P.w[2], h * P.a[5]);
+  kadd(P.s[0], h * a6); kadd(P.s[1], h * a7);
+  kadd(P.p[0], h * P.v[0].s - h * P.v[0].c);
+  kadd(P.p[1], h * P.v[1].s - h * P.v[1].c);
+  kadd(P.p[2], h * P.v[2].s - h * P.v[2].c);
+  kadd(P.th[0], h * P.s[0].s); kadd(P.th[1], h * P.s[1].s);
   {
     // q <- q (x) [cos(t/2), sin(t/2) w/|w|], t = h |w|; added as the increment q (x) (dq - 1)
-    const float n0 = st.w[0].s, n1 = st.w[1].s, n2 = st.w[2].s;
+    const float qw = P.q[0].s, qx = P.q[1].s, qy = P.q[2].s, qz = P.q[3].s;
+    const float n0 = P.w[0].s, n1 = P.w[1].s, n2 = P.w[2].s;
     const float t2 = (h * h) * (n0 * n0 + n1 * n1 + n2 * n2);
     const float sn = (0.5f * h) * (1.f - t2 * (1.f / 24.f));
     const float cm1 = -(0.125f * t2) * (1.f - t2 * (1.f / 48.f));
     const float ex = sn * n0, ey = sn * n1, ez = sn * n2;
-    const float dw = qw * cm1 - (qx * ex + qy * ey + qz * ez);
-    const float dx = qx * cm1 + (qw * ex + qy * ez - qz * ey);
-    const float dy = qy * cm1 + (qw * ey - qx * ez + qz * ex);
-    const float dz = qz * cm1 + (qw * ez + qx * ey - qy * ex);
-    kadd(st.q[0], dw); kadd(st.q[1], dx); kadd(st.q[2], dy); kadd(st.q[3], dz);
+    kadd(P.q[0], qw * cm1 - (qx * ex + qy * ey + qz * ez));
+    kadd(P.q[1], qx * cm1 + (qw * ex + qy * ez - qz * ey));
+    kadd(P.q[2], qy * cm1 + (qw * ey - qx * ez + qz * ex));
+    kadd(P.q[3], qz * cm1 + (qw * ez + qx * ey - qy * ex));
   }
+}
+
+// ---- nsub substeps as a per-lane state machine.  Every trip of the loop does at most ONE 8x8 solve per
+// lane; a lane whose active set changed simply repeats the solve in the next trip while its neighbours move on to
+// their next substep, so a warp pays max-over-lanes(nsub + extra solves) trips instead of nsub * max-over-lanes
+// (solves per substep).  qstale receives the quaternion before the last integration (Q1).
+template <int MAXIT>
+BRB_D void phys_run(const BrbModelConsts &c, Phys &P, int nsub, KF (&qstale)[4]) {
+  int sidx = 0, it = 0;
+  unsigned bits = 0xFFFFu;                       // previous substep's active set (hysteresis seed): start "all active"
+  phys_setup(c, P);
+  if (P.valid) bits = phys_active_set(c, P, bits);
+  for (;;) {
+    bool conv = true;
+    if (P.valid) {
+      phys_solve(c, P, bits);
+      const unsigned nb = phys_active_set(c, P, bits);
+      conv = (nb == bits);
+      bits = nb;
+      if (!conv && ++it >= MAXIT) { P.n_nonconv++; conv = true; }
+    } else {
+      phys_free_accel(c, P);
+    }
+    if (conv) {
+      if (sidx == nsub - 1) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) qstale[k] = P.q[k];
+      }
+      phys_finalize(c, P);
+      if (++sidx >= nsub) break;
+      phys_setup(c, P);
+      it = 0;
+      if (P.valid) bits = phys_active_set(c, P, bits);
+    }
+  }
+}
+
+// lowest wheel-rim height above the floor for the CURRENT pose (fp32), used only to group envs for the next step
+BRB_D float phys_clearance(const BrbModelConsts &c, const Phys &P) {
+  const float qw = P.q[0].s, qx = P.q[1].s, qy = P.q[2].s, qz = P.q[3].s;
+  const float nx = 2.f * (qx * qz - qw * qy), ny = 2.f * (qy * qz + qw * qx), nz = 1.f - 2.f * (qx * qx + qy * qy);
+  const float rho = sqrtf(ny * ny + nz * nz);
+  return (P.p[2].s - c.zfloor) + c.oz * nz - c.rad * rho - (c.ox + c.hl) * fabsf(nx);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -469,13 +485,13 @@ __device__ __forceinline__ unsigned long long warp_sum(unsigned v) {
 }
 #endif
 
-// One VecEnv.step for env i of the shard.  stat[6] receives {substeps, contact substeps, solves, non-converged,
-// unsupported-pose flag, done flag}.
+// One VecEnv.step for env i of the shard.  stat[8] receives {substeps, contact substeps, solves, non-converged,
+// unsupported-pose flag, done flag, group hint for the next step, contact slots in use}.
 template <int KIND>
 BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long i, const float *__restrict__ actions,
                     float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done,
                     uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs, float *__restrict__ ep_return_out,
-                    int32_t *__restrict__ ep_len_out, const double *__restrict__ replay_u, unsigned stat[6]) {
+                    int32_t *__restrict__ ep_len_out, const double *__restrict__ replay_u, unsigned stat[8]) {
   const long long N = S.n;
   // ---------------- prologue (fp64 task logic on the pre-step state) ----------------
   double qvel[8], xq[4];
@@ -511,7 +527,7 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
   double ctrl[2] = {qvel[6] + (double)act_x * 4.0, qvel[7] + (double)act_y * 4.0};   // env01_v1.py:18-23
 
   // ---------------- 250 substeps ----------------
-  Sub st;
+  Phys st;
   {
     double qn[4], nn = 0;
 #pragma unroll
@@ -531,18 +547,17 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
     }
 #pragma unroll
     for (int k = 0; k < 8; k++) st.a[k] = S.warm[k * N + i];
-    st.n_contact = st.n_solve = st.n_nonconv = 0;
+    st.n_contact = st.n_solve = st.n_nonconv = st.n_slots = 0;
   }
   const int nsub = c.frame_skip;
   KF qprev[4];
-  for (int sidx = 0; sidx < nsub; sidx++) {
-    if (sidx == nsub - 1) {
-#pragma unroll
-      for (int k = 0; k < 4; k++) qprev[k] = st.q[k];   // Q1: kinematics seen by the task logic are one substep stale
-    }
-    substep<BRB_MAXIT>(c, st);
+  phys_run<BRB_MAXIT>(c, st, nsub, qprev);
+  stat[0] = nsub; stat[1] = st.n_contact; stat[2] = st.n_solve; stat[3] = st.n_nonconv; stat[7] = st.n_slots;
+  {
+    // will this robot stay clear of the floor for the whole next step?  (grouping hint only, no effect on results)
+    const float drop = 0.005f * (fabsf(st.v[2].s) + 0.12f * (fabsf(st.w[0].s) + fabsf(st.w[1].s) + fabsf(st.w[2].s))) + 0.0005f;
+    stat[6] = phys_clearance(c, st) > drop ? 1u : 0u;
   }
-  stat[0] = nsub; stat[1] = st.n_contact; stat[2] = st.n_solve; stat[3] = st.n_nonconv;
 
   // ---------------- epilogue ----------------
   double qpos[9];
@@ -594,6 +609,7 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
 
   if (dn) {
     stat[5] = 1;
+    stat[6] = 1;   // reset pose: wheels 2 cm above the floor (Q11)
     if (terminal_obs) {
 #pragma unroll
       for (int k = 0; k < 6; k++) terminal_obs[i * 6 + k] = o[k];
@@ -624,19 +640,45 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
 }
 
 #ifndef BRB_HOST_EMU
+#ifdef BRB_MAXNREG
+#define BRB_STEP_BOUNDS __maxnreg__(BRB_MAXNREG)
+#else
+#define BRB_STEP_BOUNDS __launch_bounds__(BRB_BLOCK, BRB_MINBLOCKS)
+#endif
 template <int KIND>
-__global__ void __launch_bounds__(BRB_BLOCK) brb_step_kernel(const __grid_constant__ BrbModelConsts c, const BrbState S,
-                                                             const float *__restrict__ actions, float *__restrict__ obs,
-                                                             float *__restrict__ reward, uint8_t *__restrict__ done,
-                                                             uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs,
-                                                             float *__restrict__ ep_return_out, int32_t *__restrict__ ep_len_out,
-                                                             const double *__restrict__ replay_u) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  unsigned stat[6] = {0, 0, 0, 0, 0, 0};
-  if (i < S.n) step_env<KIND>(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat);
+__global__ void BRB_STEP_BOUNDS brb_step_kernel(const __grid_constant__ BrbModelConsts c, const BrbState S, const BrbPerm perm,
+                                                const float *__restrict__ actions, float *__restrict__ obs,
+                                                float *__restrict__ reward, uint8_t *__restrict__ done,
+                                                uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs,
+                                                float *__restrict__ ep_return_out, int32_t *__restrict__ ep_len_out,
+                                                const double *__restrict__ replay_u) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = tid < S.n;
+  // envs are visited in the order of the partition built by the previous step: robots expected to stay airborne
+  // first, grounded ones last, so a warp's lanes mostly run the same path (state columns are addressed by env id)
+  const long long i = live ? (perm.in ? (long long)perm.in[tid] : tid) : 0;
+  unsigned stat[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  if (live) step_env<KIND>(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat);
+  if (perm.out) {
+    const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
+    const unsigned m_air = __ballot_sync(0xFFFFFFFFu, live && stat[6]), m_gnd = __ballot_sync(0xFFFFFFFFu, live && !stat[6]);
+    unsigned base_a = 0, base_g = 0;
+    if (lane == 0) {
+      if (m_air) base_a = atomicAdd(&perm.cnt_out[0], __popc(m_air));
+      if (m_gnd) base_g = atomicAdd(&perm.cnt_out[1], __popc(m_gnd));
+    }
+    base_a = __shfl_sync(0xFFFFFFFFu, base_a, 0);
+    base_g = __shfl_sync(0xFFFFFFFFu, base_g, 0);
+    if (live) {
+      // grounded (expensive) robots are packed from the front so they start first; the cheap airborne ones fill the tail
+      const long long slot = stat[6] ? S.n - 1 - (long long)(base_a + __popc(m_air & below)) : (long long)(base_g + __popc(m_gnd & below));
+      perm.out[slot] = (int)i;
+    }
+    if (tid == 0) { perm.cnt_zero[0] = 0u; perm.cnt_zero[1] = 0u; }
+  }
   // statistics: one atomic per warp per counter
   const unsigned long long a0 = warp_sum(stat[0]), a1 = warp_sum(stat[1]), a2 = warp_sum(stat[2]), a3 = warp_sum(stat[3]),
-                           a4 = warp_sum(stat[4]), a5 = warp_sum(stat[5]), a6 = warp_sum(i < S.n ? 1u : 0u);
+                           a4 = warp_sum(stat[4]), a5 = warp_sum(stat[5]), a6 = warp_sum(live ? 1u : 0u), a7 = warp_sum(stat[7]);
   if ((threadIdx.x & 31) == 0) {
     atomicAdd(&S.stats[BRB_STAT_SUBSTEPS], a0);
     atomicAdd(&S.stats[BRB_STAT_CONTACT_SUBSTEPS], a1);
@@ -645,6 +687,7 @@ __global__ void __launch_bounds__(BRB_BLOCK) brb_step_kernel(const __grid_consta
     if (a4) atomicAdd(&S.stats[BRB_STAT_UNSUPPORTED], a4);
     if (a5) atomicAdd(&S.stats[BRB_STAT_EPISODES], a5);
     atomicAdd(&S.stats[BRB_STAT_ENV_STEPS], a6);
+    atomicAdd(&S.stats[BRB_STAT_CONTACT_SLOTS], a7);
   }
 }
 
@@ -707,19 +750,19 @@ __global__ void brb_ffma_probe_kernel(float *out, int iters, float a, float b) {
 
 // ---------------------------------------------------------------------------------------------------
 // launch wrappers used by the C-ABI translation unit (brb_cabi.cu)
-extern "C" void brb_launch_step(int kind, const BrbModelConsts *c, const BrbState *S, const float *actions, float *obs, float *reward,
+extern "C" void brb_launch_step(int kind, const BrbModelConsts *c, const BrbState *S, const BrbPerm *perm, const float *actions, float *obs, float *reward,
                                 uint8_t *done, uint8_t *truncated, float *terminal_obs, float *ep_return, int32_t *ep_len,
                                 const double *replay_u, cudaStream_t stream) {
   const unsigned grid = (unsigned)((S->n + BRB_BLOCK - 1) / BRB_BLOCK);
   switch (kind) {
     case BRB_ENV01_V1:
-      brb_step_kernel<BRB_ENV01_V1><<<grid, BRB_BLOCK, 0, stream>>>(*c, *S, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
+      brb_step_kernel<BRB_ENV01_V1><<<grid, BRB_BLOCK, 0, stream>>>(*c, *S, *perm, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
       break;
     case BRB_ENV01_V2:
-      brb_step_kernel<BRB_ENV01_V2><<<grid, BRB_BLOCK, 0, stream>>>(*c, *S, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
+      brb_step_kernel<BRB_ENV01_V2><<<grid, BRB_BLOCK, 0, stream>>>(*c, *S, *perm, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
       break;
     default:
-      brb_step_kernel<BRB_ENV01_V3><<<grid, BRB_BLOCK, 0, stream>>>(*c, *S, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
+      brb_step_kernel<BRB_ENV01_V3><<<grid, BRB_BLOCK, 0, stream>>>(*c, *S, *perm, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
       break;
   }
 }

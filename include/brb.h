@@ -39,6 +39,7 @@ extern "C" {
 #define BRB_STAT_UNSUPPORTED 4       /* env-steps that ended in a pose whose contacts the kernel does not model */
 #define BRB_STAT_EPISODES 5          /* episodes finished */
 #define BRB_STAT_ENV_STEPS 6
+#define BRB_STAT_CONTACT_SLOTS 7     /* sum over contact substeps of the number of wheel-floor contacts (1..4) */
 
 /* Per-model constant block, produced on the host by balance_robot_b200/model.py from the MJCF
  * (stands in for MjModel.from_xml_path, reference envs/RobotBaseEnv.py:56-65).  Passed to the

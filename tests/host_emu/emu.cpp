@@ -48,9 +48,10 @@ extern "C" void emu_reset(Emu *e, float *obs, const double *replay) {
 template <int KIND> static void step_all(Emu *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *trunc,
                                          float *tobs, float *epr, int32_t *epl, const double *replay) {
   for (long long i = 0; i < e->S.n; i++) {
-    unsigned stat[6] = {0, 0, 0, 0, 0, 0};
+    unsigned stat[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     step_env<KIND>(e->c, e->S, i, actions, obs, reward, done, trunc, tobs, epr, epl, replay, stat);
     for (int k = 0; k < 6; k++) e->stats[k] += stat[k];
+    e->stats[BRB_STAT_CONTACT_SLOTS] += stat[7];
     e->stats[BRB_STAT_ENV_STEPS] += 1;
   }
 }

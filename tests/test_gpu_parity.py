@@ -60,7 +60,7 @@ def test_native_library_is_loaded():
 def test_single_step_parity_closed_loop(spec, kind):
     env = GpuAdapter(helpers.ENV_IDS[kind], 32, 3)
     wq, wv = pc.single_step_parity(env, spec, helpers.ENV_IDS[kind], 32, 3, 150)
-    assert wq < 1e-6 and wv < 1e-6
+    assert wq < 1e-5 and wv < 1e-5          # the north-star tolerance (typical: 1e-8 .. 1e-6)
     env.close()
 
 
