@@ -14,6 +14,8 @@ extern "C" {
 void brb_launch_step(int kind, const BrbModelConsts *c, const BrbState *S, const BrbPerm *perm, const float *actions, float *obs, float *reward,
                      uint8_t *done, uint8_t *truncated, float *terminal_obs, float *ep_return, int32_t *ep_len,
                      const double *replay_u, cudaStream_t stream);
+void brb_launch_group(long long n, const uint8_t *key, const unsigned *hist, unsigned *cursor, int *order, unsigned *hist_zero,
+                      unsigned *cursor_zero, cudaStream_t stream);
 void brb_launch_reset(int kind, const BrbState *S, float *obs, const double *replay_u, cudaStream_t stream);
 void brb_launch_get_state(const BrbState *S, double *qpos, double *qvel, double *xquat, cudaStream_t stream);
 void brb_launch_set_state(const BrbState *S, const double *qpos, const double *qvel, cudaStream_t stream);
@@ -33,10 +35,10 @@ struct BrbEnv {
   BrbState S;
   void *arena;          // one allocation backing every SoA column
   int64_t launches;
-  int *perm[2];         // double-buffered visit order (airborne-first partition), see BrbPerm
-  unsigned *perm_cnt;   // [2][2]
-  int parity;           // which perm buffer the next step reads; -1 = identity (right after reset_all / set_state)
-  int sort_envs;
+  int *order;           // [N] visit order of the next step (see BrbPerm); valid when have_order
+  uint8_t *keys;        // [N] group keys published by the last step
+  unsigned *hist;       // [2][32] double-buffered histogram, [2][32] cursors behind it
+  int have_order, parity, sort_envs;
   // device staging for brb_env_step_host
   float *d_actions, *d_obs, *d_reward, *d_tobs, *d_epret;
   uint8_t *d_done, *d_trunc;
@@ -92,7 +94,7 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
   const size_t N = (size_t)n;
   const size_t sz[] = {
       align_up(9 * N * 8), align_up(8 * N * 8), align_up(4 * N * 8), align_up(8 * N * 4), align_up(N * 8), align_up(N * 8),
-      align_up(3 * N * 8), align_up(N * 4), align_up(N * 4), align_up(N * 4), align_up(BRB_NSTATS * 8), align_up(N * 4), align_up(N * 4), align_up(16),
+      align_up(3 * N * 8), align_up(N * 4), align_up(N * 4), align_up(N * 4), align_up(BRB_NSTATS * 8), align_up(N * 4), align_up(N), align_up(4 * 32 * 4),
       // staging
       align_up(2 * N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(N), align_up(N), align_up(N * 4)};
   size_t total = 0;
@@ -113,9 +115,9 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
   e->S.ep_len = TAKE(int);
   e->S.event = TAKE(uint32_t);
   e->S.stats = TAKE(unsigned long long);
-  e->perm[0] = TAKE(int);
-  e->perm[1] = TAKE(int);
-  e->perm_cnt = TAKE(unsigned);
+  e->order = TAKE(int);
+  e->keys = TAKE(uint8_t);
+  e->hist = TAKE(unsigned);
   e->d_actions = TAKE(float);
   e->d_obs = TAKE(float);
   e->d_reward = TAKE(float);
@@ -129,7 +131,8 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
   e->S.env0 = env_id_offset;
   e->S.seed = seed;
   e->S.time_table = m->time_table;
-  e->parity = -1;
+  e->parity = 0;
+  e->have_order = 0;
   e->sort_envs = getenv("BRB_NO_SORT") ? 0 : 1;
   if (cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaFree(e->arena); free(e); return BRB_ECUDA; }
   *out = e;
@@ -147,18 +150,26 @@ extern "C" void brb_env_destroy(BrbEnv *e) {
 extern "C" int64_t brb_env_num_envs(const BrbEnv *e) { return e ? e->S.n : 0; }
 extern "C" int64_t brb_env_num_launches(const BrbEnv *e) { return e ? e->launches : 0; }
 
-// Visit order for the next step launch; flips the double buffer.  All launches of one env object must be
-// stream-ordered with respect to each other (same stream or externally synchronised), as for any stateful env.
-static BrbPerm next_perm(BrbEnv *e) {
-  BrbPerm p = {nullptr, nullptr, nullptr, nullptr};
-  if (!e->sort_envs) return p;
-  const int rd = e->parity < 0 ? 0 : e->parity, wr = rd ^ 1;
-  p.in = e->parity < 0 ? nullptr : e->perm[rd];
-  p.out = e->perm[wr];
-  p.cnt_out = e->perm_cnt + 2 * wr;
-  p.cnt_zero = e->perm_cnt + 2 * rd;
-  e->parity = wr;
-  return p;
+// One VecEnv.step = the fused step kernel + the (tiny) grouping kernel that sorts the envs for the next step.
+// All launches of one env object must be stream-ordered with respect to each other, as for any stateful env.
+static void launch_step(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,
+                        float *terminal_obs, float *ep_return, int32_t *ep_len, const double *replay_u, cudaStream_t stream) {
+  BrbPerm perm = {nullptr, nullptr, nullptr};
+  unsigned *hist = e->hist + 32 * e->parity, *cursor = e->hist + 64 + 32 * e->parity;
+  if (e->sort_envs) {
+    perm.in = e->have_order ? e->order : nullptr;
+    perm.key_out = e->keys;
+    perm.hist = hist;
+  }
+  brb_launch_step(e->model->consts.env_kind, &e->model->consts, &e->S, &perm, actions, obs, reward, done, truncated, terminal_obs,
+                  ep_return, ep_len, replay_u, stream);
+  e->launches++;
+  if (e->sort_envs) {
+    brb_launch_group(e->S.n, e->keys, hist, cursor, e->order, e->hist + 32 * (e->parity ^ 1), e->hist + 64 + 32 * (e->parity ^ 1), stream);
+    e->launches++;
+    e->have_order = 1;
+    e->parity ^= 1;
+  }
 }
 
 extern "C" int brb_env_reset_all(BrbEnv *e, float *obs, const double *replay_u_reset, void *stream) {
@@ -166,6 +177,7 @@ extern "C" int brb_env_reset_all(BrbEnv *e, float *obs, const double *replay_u_r
   CK(cudaSetDevice(e->model->device));
   brb_launch_reset(e->model->consts.env_kind, &e->S, obs, replay_u_reset, (cudaStream_t)stream);
   e->launches++;
+  e->have_order = 0;
   CK(cudaGetLastError());
   return BRB_OK;
 }
@@ -174,10 +186,7 @@ extern "C" int brb_env_step(BrbEnv *e, const float *actions, float *obs, float *
                             float *terminal_obs, float *ep_return, int32_t *ep_len, const double *replay_u, void *stream) {
   if (!e || !actions || !obs) return BRB_EINVAL;
   CK(cudaSetDevice(e->model->device));
-  BrbPerm perm = next_perm(e);
-  brb_launch_step(e->model->consts.env_kind, &e->model->consts, &e->S, &perm, actions, obs, reward, done, truncated, terminal_obs,
-                  ep_return, ep_len, replay_u, (cudaStream_t)stream);
-  e->launches++;
+  launch_step(e, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u, (cudaStream_t)stream);
   CK(cudaGetLastError());
   return BRB_OK;
 }
@@ -189,10 +198,7 @@ extern "C" int brb_env_step_host(BrbEnv *e, const float *actions, float *obs, fl
   const size_t N = (size_t)e->S.n;
   cudaStream_t s = e->host_stream;
   CK(cudaMemcpyAsync(e->d_actions, actions, 2 * N * sizeof(float), cudaMemcpyHostToDevice, s));
-  BrbPerm perm = next_perm(e);
-  brb_launch_step(e->model->consts.env_kind, &e->model->consts, &e->S, &perm, e->d_actions, e->d_obs, e->d_reward, e->d_done, e->d_trunc,
-                  e->d_tobs, e->d_epret, e->d_eplen, nullptr, s);
-  e->launches++;
+  launch_step(e, e->d_actions, e->d_obs, e->d_reward, e->d_done, e->d_trunc, e->d_tobs, e->d_epret, e->d_eplen, nullptr, s);
   CK(cudaGetLastError());
   CK(cudaMemcpyAsync(obs, e->d_obs, 6 * N * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (reward) CK(cudaMemcpyAsync(reward, e->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, s));

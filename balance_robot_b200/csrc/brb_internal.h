@@ -31,12 +31,13 @@ struct BrbState {
   unsigned long long *stats; // [BRB_NSTATS]
 };
 
-// Visit order of the step kernel (double-buffered): in = order for this launch (NULL = identity), out = order the
-// launch builds for the next one (airborne robots packed from the front, grounded from the back).
+// Visit order of the step kernel: `in` = order for this launch (NULL = identity).  The launch publishes a group key per
+// env (0 = far airborne, 1.. = by wheel-rim contact pattern) plus a histogram; brb_group_kernel counting-sorts them into the
+// next launch's order, so that the lanes of a warp mostly run the same contact path.
+#define BRB_NGROUPS 18
 struct BrbPerm {
   const int *in;
-  int *out;
-  unsigned *cnt_out;   // [2] slot counters for `out`, zero on entry
-  unsigned *cnt_zero;  // [2] the other buffer's counters, cleared for the next launch
+  uint8_t *key_out;    // [N]
+  unsigned *hist;      // [32] accumulated by the step kernel, zero on entry
 };
 #endif

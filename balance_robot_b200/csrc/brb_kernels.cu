@@ -186,6 +186,10 @@ BRB_D void reset_env(const BrbState &S, long long i, const double u[16], float o
 // registers (a run-time contact index sends H[] to local memory — measured in profiles/r1a).
 #define LT(i, j) ((i) * ((i) + 1) / 2 + (j))   // packed lower-triangular index
 
+#ifdef BRB_TRIPSTATS
+__device__ unsigned long long g_trip[8];   // debug: warp-trips, lane-trips, warp-trips with a solve, lanes solving
+#endif
+
 struct Phys {
   // ---- state carried across substeps
   KF p[3], q[4], th[2], v[3], w[3], s[2];   // world pos, quat (w,x,y,z), wheel angles, world lin vel, body ang vel, wheel speeds
@@ -440,11 +444,22 @@ BRB_D void phys_finalize(const BrbModelConsts &c, Phys &P) {
 template <int MAXIT>
 BRB_D void phys_run(const BrbModelConsts &c, Phys &P, int nsub, KF (&qstale)[4]) {
   int sidx = 0, it = 0;
-  unsigned bits = 0xFFFFu;                       // previous substep's active set (hysteresis seed): start "all active"
+  // The active set of a new substep is seeded with the previous substep's converged set (rows of a contact that just
+  // appeared start "all active"): right ~97 % of the time, and the post-solve check below catches the rest.
+  unsigned bits = 0xFFFFu;
   phys_setup(c, P);
-  if (P.valid) bits = phys_active_set(c, P, bits);
   for (;;) {
     bool conv = true;
+#ifdef BRB_TRIPSTATS
+    {
+      const unsigned act = __activemask();
+      const unsigned nv = __popc(__ballot_sync(act, P.valid != 0u));
+      if ((threadIdx.x & 31u) == (unsigned)(__ffs(act) - 1)) {
+        atomicAdd(&g_trip[0], 1ull); atomicAdd(&g_trip[1], (unsigned long long)__popc(act));
+        if (nv) { atomicAdd(&g_trip[2], 1ull); atomicAdd(&g_trip[3], (unsigned long long)nv); }
+      }
+    }
+#endif
     if (P.valid) {
       phys_solve(c, P, bits);
       const unsigned nb = phys_active_set(c, P, bits);
@@ -461,11 +476,23 @@ BRB_D void phys_run(const BrbModelConsts &c, Phys &P, int nsub, KF (&qstale)[4])
       }
       phys_finalize(c, P);
       if (++sidx >= nsub) break;
+      const unsigned was = P.valid;
       phys_setup(c, P);
       it = 0;
-      if (P.valid) bits = phys_active_set(c, P, bits);
+      // slots that were not in contact a substep ago start with all four pyramid rows active
+      const unsigned fresh = P.valid & ~was;
+      bits |= ((fresh & 1u) ? 0xFu : 0u) | ((fresh & 2u) ? 0xF0u : 0u) | ((fresh & 4u) ? 0xF00u : 0u) | ((fresh & 8u) ? 0xF000u : 0u);
     }
   }
+}
+
+// contact-slot mask (bit = 2*wheel + rim end) -> bucket rank, ordered by number of contacts, then by pattern
+BRB_D unsigned group_rank(unsigned mask) {
+  //                         mask: 0  1  2  3  4  5   6  7   8  9  10  11  12  13  14  15
+  const unsigned long long lut = 0x0ull | (1ull << 4) | (3ull << 8) | (6ull << 12) | (2ull << 16) | (5ull << 20) | (9ull << 24) |
+                                 (11ull << 28) | (4ull << 32) | (10ull << 36) | (8ull << 40) | (13ull << 44) | (7ull << 48) |
+                                 (12ull << 52) | (14ull << 56) | (15ull << 60);
+  return (unsigned)((lut >> (4 * (mask & 15u))) & 15ull);
 }
 
 // lowest wheel-rim height above the floor for the CURRENT pose (fp32), used only to group envs for the next step
@@ -554,9 +581,11 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
   phys_run<BRB_MAXIT>(c, st, nsub, qprev);
   stat[0] = nsub; stat[1] = st.n_contact; stat[2] = st.n_solve; stat[3] = st.n_nonconv; stat[7] = st.n_slots;
   {
-    // will this robot stay clear of the floor for the whole next step?  (grouping hint only, no effect on results)
+    // group key for the next step's visit order (no effect on results): robots are bucketed by which wheel-rim contact
+    // slots they ended the step with, airborne ones by whether they can reach the floor within one more step
     const float drop = 0.005f * (fabsf(st.v[2].s) + 0.12f * (fabsf(st.w[0].s) + fabsf(st.w[1].s) + fabsf(st.w[2].s))) + 0.0005f;
-    stat[6] = phys_clearance(c, st) > drop ? 1u : 0u;
+    const bool far = phys_clearance(c, st) > drop;
+    stat[6] = (st.valid == 0u && far) ? 0u : 1u + group_rank(st.valid);
   }
 
   // ---------------- epilogue ----------------
@@ -609,7 +638,7 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
 
   if (dn) {
     stat[5] = 1;
-    stat[6] = 1;   // reset pose: wheels 2 cm above the floor (Q11)
+    stat[6] = 0;   // reset pose: wheels ~2 cm above the floor (Q11)
     if (terminal_obs) {
 #pragma unroll
       for (int k = 0; k < 6; k++) terminal_obs[i * 6 + k] = o[k];
@@ -659,22 +688,12 @@ __global__ void BRB_STEP_BOUNDS brb_step_kernel(const __grid_constant__ BrbModel
   const long long i = live ? (perm.in ? (long long)perm.in[tid] : tid) : 0;
   unsigned stat[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   if (live) step_env<KIND>(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat);
-  if (perm.out) {
-    const unsigned lane = threadIdx.x & 31u, below = (1u << lane) - 1u;
-    const unsigned m_air = __ballot_sync(0xFFFFFFFFu, live && stat[6]), m_gnd = __ballot_sync(0xFFFFFFFFu, live && !stat[6]);
-    unsigned base_a = 0, base_g = 0;
-    if (lane == 0) {
-      if (m_air) base_a = atomicAdd(&perm.cnt_out[0], __popc(m_air));
-      if (m_gnd) base_g = atomicAdd(&perm.cnt_out[1], __popc(m_gnd));
-    }
-    base_a = __shfl_sync(0xFFFFFFFFu, base_a, 0);
-    base_g = __shfl_sync(0xFFFFFFFFu, base_g, 0);
-    if (live) {
-      // grounded (expensive) robots are packed from the front so they start first; the cheap airborne ones fill the tail
-      const long long slot = stat[6] ? S.n - 1 - (long long)(base_a + __popc(m_air & below)) : (long long)(base_g + __popc(m_gnd & below));
-      perm.out[slot] = (int)i;
-    }
-    if (tid == 0) { perm.cnt_zero[0] = 0u; perm.cnt_zero[1] = 0u; }
+  if (perm.key_out) {
+    // publish this robot's group key and add it to the histogram the grouping kernel turns into bucket offsets
+    const unsigned key = live ? stat[6] : 31u;
+    if (live) perm.key_out[i] = (uint8_t)key;
+    const unsigned same = __match_any_sync(0xFFFFFFFFu, key);
+    if (live && (threadIdx.x & 31u) == (unsigned)(__ffs(same) - 1)) atomicAdd(&perm.hist[key], (unsigned)__popc(same));
   }
   // statistics: one atomic per warp per counter
   const unsigned long long a0 = warp_sum(stat[0]), a1 = warp_sum(stat[1]), a2 = warp_sum(stat[2]), a3 = warp_sum(stat[3]),
@@ -689,6 +708,25 @@ __global__ void BRB_STEP_BOUNDS brb_step_kernel(const __grid_constant__ BrbModel
     atomicAdd(&S.stats[BRB_STAT_ENV_STEPS], a6);
     atomicAdd(&S.stats[BRB_STAT_CONTACT_SLOTS], a7);
   }
+}
+
+// Counting sort of the envs by group key -> visit order of the next step.  hist[] was accumulated by the step kernel;
+// order inside a bucket is arbitrary (atomic cursor) and irrelevant to the results, which are per-env deterministic.
+__global__ void brb_group_kernel(long long n, const uint8_t *__restrict__ key, const unsigned *__restrict__ hist, unsigned *cursor,
+                                 int *__restrict__ order, unsigned *hist_zero, unsigned *cursor_zero) {
+  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = tid < n;
+  const unsigned k = live ? key[tid] : 31u;
+  unsigned base = 0;
+  for (unsigned j = 0; j < k && j < BRB_NGROUPS; j++) base += hist[j];
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned same = __match_any_sync(0xFFFFFFFFu, k);
+  const unsigned leader = (unsigned)(__ffs(same) - 1);
+  unsigned off = 0;
+  if (live && lane == leader) off = atomicAdd(&cursor[k], (unsigned)__popc(same));
+  off = __shfl_sync(0xFFFFFFFFu, off, leader);
+  if (live) order[base + off + __popc(same & ((1u << lane) - 1u))] = (int)tid;
+  if (tid < BRB_NGROUPS) { hist_zero[tid] = 0u; cursor_zero[tid] = 0u; }
 }
 
 template <int KIND>
@@ -765,6 +803,15 @@ extern "C" void brb_launch_step(int kind, const BrbModelConsts *c, const BrbStat
       brb_step_kernel<BRB_ENV01_V3><<<grid, BRB_BLOCK, 0, stream>>>(*c, *S, *perm, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
       break;
   }
+}
+
+#ifdef BRB_TRIPSTATS
+extern "C" void brb_tripstats(unsigned long long *out) { cudaMemcpyFromSymbol(out, g_trip, sizeof(unsigned long long) * 8); }
+#endif
+
+extern "C" void brb_launch_group(long long n, const uint8_t *key, const unsigned *hist, unsigned *cursor, int *order, unsigned *hist_zero,
+                                 unsigned *cursor_zero, cudaStream_t stream) {
+  brb_group_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, key, hist, cursor, order, hist_zero, cursor_zero);
 }
 
 extern "C" void brb_launch_reset(int kind, const BrbState *S, float *obs, const double *replay_u, cudaStream_t stream) {

@@ -50,6 +50,9 @@ OBSERVATION_SPACE = Box([-2 * np.pi, -2 * np.pi, -1.0, -1.0, -1.0, -1.0], [2 * n
 ACTION_SPACE = Box([-1.0, -1.0], [1.0, 1.0])
 
 
+_NO_INFO: dict = {}
+
+
 class InfoBatch:
     """Tensor-valued infos of one step; `infos[i]` materialises the SB3 dict for env i."""
 
@@ -155,12 +158,16 @@ class BalanceVecEnv:
                                             self._h_done.data_ptr(), self._h_trunc.data_ptr(), self._h_tobs.data_ptr(),
                                             self._h_epr.data_ptr(), self._h_epl.data_ptr()), "brb_env_step_host")
             done = self._h_done.numpy().astype(bool)
-            infos: List[dict] = [{} for _ in range(self.num_envs)]
-            for i in np.flatnonzero(done):
-                infos[i] = {"terminal_observation": self._h_tobs.numpy()[i].copy(),
-                            "TimeLimit.truncated": bool(self._h_trunc.numpy()[i]),
-                            "episode": {"r": float(self._h_epr.numpy()[i]), "l": int(self._h_epl.numpy()[i]),
-                                        "t": round(time.time() - self._t0, 6)}}
+            # SB3 only reads infos: envs that did not finish share one empty dict, so this stays O(#done) per step
+            infos: List[dict] = [_NO_INFO] * self.num_envs
+            idx = np.flatnonzero(done)
+            if idx.size:
+                tobs, trunc = self._h_tobs.numpy()[idx].copy(), self._h_trunc.numpy()[idx]
+                epr, epl = self._h_epr.numpy()[idx], self._h_epl.numpy()[idx]
+                t = round(time.time() - self._t0, 6)
+                for j, i in enumerate(idx.tolist()):
+                    infos[i] = {"terminal_observation": tobs[j], "TimeLimit.truncated": bool(trunc[j]),
+                                "episode": {"r": float(epr[j]), "l": int(epl[j]), "t": t}}
             return self._h_obs.numpy().copy(), self._h_rew.numpy().copy(), done, infos
         a = self._actions
         if not isinstance(a, torch.Tensor):
