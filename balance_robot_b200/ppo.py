@@ -1,0 +1,316 @@
+"""On-device PPO for the batched balance-robot environments.
+
+The reference trains with stable_baselines3.PPO("MlpPolicy", env, device='cpu') and SB3's defaults
+(sb_rl.py:63-71): MlpPolicy pi=[64,64] vf=[64,64] tanh, state-independent log_std (init 0), orthogonal init
+(gains sqrt(2) / 0.01 / 1), n_steps 2048, batch 64, 10 epochs, lr 3e-4, gamma 0.99, lambda 0.95, clip 0.2,
+vf_coef 0.5, ent_coef 0, max_grad_norm 0.5, Adam eps 1e-5, per-minibatch advantage normalisation, actions
+clipped to the action space for the env while the buffer keeps the unclipped sample, and gamma * V(terminal
+observation) added to the reward of time-limit truncations.  This module keeps those semantics and
+hyper-parameters but runs the rollout buffer, GAE and the updates on the GPU next to the env kernels, with
+rollout / batch sizes that scale with the number of envs (SB3's 2048 x 1 env is for a single CPU env).
+
+Multi-GPU: one process per GPU (torchrun), envs sharded by rank; the only collectives are one flat-gradient
+all-reduce per minibatch and one all-reduce of the rollout statistics (NCCL over NVLink; gloo in CPU tests).
+The policy state-dict uses SB3's key names so checkpoints can be exchanged with the reference tooling.
+"""
+from __future__ import annotations
+
+import dataclasses
+import io
+import json
+import math
+import pathlib
+import time
+import zipfile
+from typing import Callable, Dict, Optional
+
+import torch
+import torch.nn as nn
+
+
+# ------------------------------------------------------------------------------------------------ policy
+class _MlpExtractor(nn.Module):
+    def __init__(self, obs_dim: int, hidden: int):
+        super().__init__()
+        self.policy_net = nn.Sequential(nn.Linear(obs_dim, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh())
+        self.value_net = nn.Sequential(nn.Linear(obs_dim, hidden), nn.Tanh(), nn.Linear(hidden, hidden), nn.Tanh())
+
+
+class MlpPolicy(nn.Module):
+    """SB3 ActorCriticPolicy("MlpPolicy") for Box observations / actions; same parameter names and init."""
+
+    def __init__(self, obs_dim: int = 6, act_dim: int = 2, hidden: int = 64, log_std_init: float = 0.0):
+        super().__init__()
+        self.mlp_extractor = _MlpExtractor(obs_dim, hidden)
+        self.action_net = nn.Linear(hidden, act_dim)
+        self.value_net = nn.Linear(hidden, 1)
+        self.log_std = nn.Parameter(torch.full((act_dim,), float(log_std_init)))
+        for mod, gain in ((self.mlp_extractor, math.sqrt(2)), (self.action_net, 0.01), (self.value_net, 1.0)):
+            for m in mod.modules():
+                if isinstance(m, nn.Linear):
+                    nn.init.orthogonal_(m.weight, gain=gain)
+                    nn.init.zeros_(m.bias)
+
+    def _dist(self, obs):
+        mean = self.action_net(self.mlp_extractor.policy_net(obs))
+        return mean, self.log_std.expand_as(mean)
+
+    def value(self, obs):
+        return self.value_net(self.mlp_extractor.value_net(obs)).squeeze(-1)
+
+    @staticmethod
+    def _log_prob(actions, mean, log_std):
+        var = torch.exp(2 * log_std)
+        return (-((actions - mean) ** 2) / (2 * var) - log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
+
+    @torch.no_grad()
+    def act(self, obs, deterministic: bool = False, generator: Optional[torch.Generator] = None):
+        mean, log_std = self._dist(obs)
+        if deterministic:
+            actions = mean
+        else:
+            noise = torch.randn(mean.shape, device=mean.device, dtype=mean.dtype, generator=generator)
+            actions = mean + noise * torch.exp(log_std)
+        return actions, self.value(obs), self._log_prob(actions, mean, log_std)
+
+    def evaluate_actions(self, obs, actions):
+        mean, log_std = self._dist(obs)
+        entropy = (0.5 + 0.5 * math.log(2 * math.pi) + log_std).sum(-1)
+        return self.value(obs), self._log_prob(actions, mean, log_std), entropy
+
+    def predict(self, obs, deterministic: bool = True):
+        """SB3-style predict(): returns (clipped actions, None)."""
+        a, _, _ = self.act(torch.as_tensor(obs, device=self.log_std.device, dtype=torch.float32), deterministic)
+        return a.clamp(-1.0, 1.0), None
+
+
+# ------------------------------------------------------------------------------------------------ GAE
+def compute_gae(rewards, values, dones, last_values, gamma: float, lam: float):
+    """SB3 RolloutBuffer.compute_returns_and_advantage.  rewards/values/dones: [T, N]; dones[t] = episode ended at t
+    (so the value of step t+1 belongs to a new episode)."""
+    T = rewards.shape[0]
+    adv = torch.zeros_like(rewards)
+    last = torch.zeros_like(last_values)
+    for t in reversed(range(T)):
+        next_values = last_values if t == T - 1 else values[t + 1]
+        nonterminal = 1.0 - dones[t]
+        delta = rewards[t] + gamma * next_values * nonterminal - values[t]
+        last = delta + gamma * lam * nonterminal * last
+        adv[t] = last
+    return adv, adv + values
+
+
+# ------------------------------------------------------------------------------------------------ trainer
+@dataclasses.dataclass
+class PPOConfig:
+    n_steps: int = 32               # rollout length per env (SB3: 2048 for ONE env)
+    n_epochs: int = 10
+    n_minibatches: int = 4          # SB3: batch_size 64 -> 32 minibatches; here the count is fixed instead
+    learning_rate: float = 3e-4
+    gamma: float = 0.99
+    gae_lambda: float = 0.95
+    clip_range: float = 0.2
+    vf_coef: float = 0.5
+    ent_coef: float = 0.0
+    max_grad_norm: float = 0.5
+    adam_eps: float = 1e-5
+    normalize_advantage: bool = True
+    seed: int = 0
+
+
+class PPO:
+    def __init__(self, env, config: PPOConfig = PPOConfig(), policy: Optional[MlpPolicy] = None, device=None,
+                 rank: int = 0, world_size: int = 1):
+        self.env, self.cfg, self.rank, self.world = env, config, rank, world_size
+        self.device = torch.device(device if device is not None else getattr(env, "device", "cpu"))
+        torch.manual_seed(config.seed)          # identical initial weights on every rank
+        self.policy = (policy or MlpPolicy()).to(self.device)
+        self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=config.learning_rate, eps=config.adam_eps)
+        self.gen = torch.Generator(device=self.device).manual_seed(config.seed * 1000003 + rank)
+        self.num_timesteps = 0
+        self._obs = None
+        self.ep_stats = {"return_sum": 0.0, "len_sum": 0.0, "count": 0.0}
+        n, T = env.num_envs, config.n_steps
+        dv = self.device
+        self.buf = {"obs": torch.zeros((T, n, 6), device=dv), "actions": torch.zeros((T, n, 2), device=dv),
+                    "logp": torch.zeros((T, n), device=dv), "values": torch.zeros((T, n), device=dv),
+                    "rewards": torch.zeros((T, n), device=dv), "dones": torch.zeros((T, n), device=dv)}
+
+    # ---- distributed helpers (no-ops for world_size 1)
+    def _all_reduce_(self, t: torch.Tensor) -> torch.Tensor:
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return t
+
+    def _sync_grads(self) -> None:
+        if self.world == 1:
+            return
+        params = [p for p in self.policy.parameters() if p.grad is not None]
+        flat = torch.cat([p.grad.reshape(-1) for p in params])
+        self._all_reduce_(flat).div_(self.world)
+        off = 0
+        for p in params:
+            k = p.numel()
+            p.grad.copy_(flat[off:off + k].view_as(p))
+            off += k
+
+    # ---- rollout
+    def collect_rollouts(self) -> Dict[str, float]:
+        cfg, env, b = self.cfg, self.env, self.buf
+        if self._obs is None:
+            self._obs = torch.as_tensor(env.reset(), device=self.device, dtype=torch.float32).clone()
+        ep_ret = torch.zeros((), device=self.device, dtype=torch.float64)
+        ep_len = torch.zeros((), device=self.device, dtype=torch.float64)
+        ep_cnt = torch.zeros((), device=self.device, dtype=torch.float64)
+        for t in range(cfg.n_steps):
+            actions, values, logp = self.policy.act(self._obs, generator=self.gen)
+            b["obs"][t].copy_(self._obs)
+            b["actions"][t].copy_(actions)
+            b["values"][t].copy_(values)
+            b["logp"][t].copy_(logp)
+            obs, rew, done, infos = env.step(actions.clamp(-1.0, 1.0))      # SB3 clips for the env only
+            done_f = done.to(torch.float32)
+            rew = rew.clone()
+            # TimeLimit bootstrap: reward += gamma * V(terminal_observation) where the episode was truncated
+            trunc = infos.truncated.to(torch.bool) if hasattr(infos, "truncated") else None
+            if trunc is not None and bool(trunc.any()):
+                with torch.no_grad():
+                    tv = self.policy.value(infos.terminal_observation)
+                rew = rew + cfg.gamma * tv * trunc.to(rew.dtype)
+            b["rewards"][t].copy_(rew)
+            b["dones"][t].copy_(done_f)
+            if hasattr(infos, "episode_return"):
+                d64 = done_f.double()
+                ep_ret += (infos.episode_return.double() * d64).sum()
+                ep_len += (infos.episode_length.double() * d64).sum()
+                ep_cnt += d64.sum()
+            self._obs = obs.clone()
+        with torch.no_grad():
+            last_values = self.policy.value(self._obs)
+        adv, ret = compute_gae(b["rewards"], b["values"], b["dones"], last_values, cfg.gamma, cfg.gae_lambda)
+        b["adv"], b["ret"] = adv, ret
+        self.num_timesteps += cfg.n_steps * env.num_envs * self.world
+        stats = self._all_reduce_(torch.stack([ep_ret, ep_len, ep_cnt]))
+        r, l, c = (float(x) for x in stats.tolist())
+        self.ep_stats = {"return_sum": r, "len_sum": l, "count": c}
+        return {"ep_rew_mean": r / c if c else float("nan"), "ep_len_mean": l / c if c else float("nan"), "episodes": c}
+
+    # ---- update
+    def train(self) -> Dict[str, float]:
+        cfg, b = self.cfg, self.buf
+        T, n = b["rewards"].shape
+        flat = {k: v.reshape(T * n, *v.shape[2:]) for k, v in b.items()}
+        total = T * n
+        mb = total // cfg.n_minibatches
+        logs = torch.zeros(4, device=self.device)     # policy_loss, value_loss, approx_kl, clip_fraction (summed on device)
+        updates = 0
+        for _ in range(cfg.n_epochs):
+            perm = torch.randperm(total, device=self.device, generator=self.gen)
+            for k in range(cfg.n_minibatches):
+                idx = perm[k * mb:(k + 1) * mb]
+                adv = flat["adv"][idx]
+                if cfg.normalize_advantage and adv.numel() > 1:
+                    adv = (adv - adv.mean()) / (adv.std() + 1e-8)
+                values, logp, entropy = self.policy.evaluate_actions(flat["obs"][idx], flat["actions"][idx])
+                ratio = torch.exp(logp - flat["logp"][idx])
+                pl = -torch.min(adv * ratio, adv * torch.clamp(ratio, 1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+                vl = torch.nn.functional.mse_loss(flat["ret"][idx], values)
+                loss = pl + cfg.vf_coef * vl - cfg.ent_coef * entropy.mean()
+                self.optimizer.zero_grad(set_to_none=False)
+                loss.backward()
+                self._sync_grads()
+                torch.nn.utils.clip_grad_norm_(self.policy.parameters(), cfg.max_grad_norm)
+                self.optimizer.step()
+                with torch.no_grad():
+                    lr_ = logp - flat["logp"][idx]
+                    logs += torch.stack([pl.detach(), vl.detach(), ((torch.exp(lr_) - 1) - lr_).mean(),
+                                         ((ratio - 1).abs() > cfg.clip_range).float().mean()])
+                updates += 1
+        vals = (logs / max(1, updates)).tolist()
+        return dict(zip(("policy_loss", "value_loss", "approx_kl", "clip_fraction"), vals))
+
+    def learn(self, total_timesteps: int, callback: Optional[Callable[["PPO", Dict[str, float]], bool]] = None,
+              log_interval: int = 1, writer=None, verbose: int = 1) -> "PPO":
+        it, t0 = 0, time.time()
+        while self.num_timesteps < total_timesteps:
+            roll = self.collect_rollouts()
+            upd = self.train()
+            it += 1
+            fps = self.num_timesteps / max(1e-9, time.time() - t0)
+            rec = dict(roll, **upd, fps=fps, total_timesteps=self.num_timesteps, iterations=it)
+            if self.rank == 0:
+                if writer is not None:        # TensorBoard scalar names follow SB3
+                    writer.add_scalar("rollout/ep_rew_mean", rec["ep_rew_mean"], self.num_timesteps)
+                    writer.add_scalar("rollout/ep_len_mean", rec["ep_len_mean"], self.num_timesteps)
+                    writer.add_scalar("time/fps", fps, self.num_timesteps)
+                    writer.add_scalar("train/approx_kl", rec["approx_kl"], self.num_timesteps)
+                    writer.add_scalar("train/value_loss", rec["value_loss"], self.num_timesteps)
+                if verbose and it % log_interval == 0:
+                    print(f"[ppo] it {it:4d} steps {self.num_timesteps:>12,d} fps {fps:,.0f} ep_rew_mean {rec['ep_rew_mean']:.2f} "
+                          f"ep_len_mean {rec['ep_len_mean']:.1f} kl {rec['approx_kl']:.4f} vloss {rec['value_loss']:.3f}", flush=True)
+            if callback is not None and callback(self, rec) is False:
+                break
+        return self
+
+    # ---- checkpoints: zip laid out like SB3's (data / policy.pth / policy.optimizer.pth / pytorch_variables.pth)
+    def save(self, path) -> pathlib.Path:
+        path = pathlib.Path(path)
+        if path.suffix != ".zip":
+            path = path.with_suffix(".zip")
+        path.parent.mkdir(parents=True, exist_ok=True)
+        data = {"policy_class": "MlpPolicy", "algo": "PPO", "num_timesteps": self.num_timesteps,
+                "hyper_parameters": dataclasses.asdict(self.cfg), "observation_dim": 6, "action_dim": 2,
+                "format": "balance_robot_b200 (SB3-layout zip; state-dict keys follow SB3's ActorCriticPolicy)"}
+
+        def blob(obj):
+            bio = io.BytesIO()
+            torch.save(obj, bio)
+            return bio.getvalue()
+        with zipfile.ZipFile(path, "w") as z:
+            z.writestr("data", json.dumps(data, indent=1))
+            z.writestr("policy.pth", blob({k: v.detach().cpu() for k, v in self.policy.state_dict().items()}))
+            z.writestr("policy.optimizer.pth", blob(self.optimizer.state_dict()))
+            z.writestr("pytorch_variables.pth", blob(None))
+            z.writestr("_stable_baselines3_version", "balance_robot_b200-1.0")
+        return path
+
+    @classmethod
+    def load(cls, path, env, config: Optional[PPOConfig] = None, **kw) -> "PPO":
+        path = pathlib.Path(path)
+        if not path.exists():
+            raise RuntimeError(f"model file {path} does not exist")        # mirrors sb_rl.py:100-101
+        with zipfile.ZipFile(path) as z:
+            data = json.loads(z.read("data"))
+            sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu")
+            opt = torch.load(io.BytesIO(z.read("policy.optimizer.pth")), map_location="cpu") if "policy.optimizer.pth" in z.namelist() else None
+        cfg = config or PPOConfig(**{k: v for k, v in data.get("hyper_parameters", {}).items() if k in PPOConfig.__dataclass_fields__})
+        self = cls(env, cfg, **kw)
+        self.policy.load_state_dict(sd)
+        if opt:
+            try:
+                self.optimizer.load_state_dict(opt)
+            except Exception:
+                pass
+        self.num_timesteps = int(data.get("num_timesteps", 0))
+        return self
+
+
+@torch.no_grad()
+def evaluate_policy(policy: MlpPolicy, env, n_eval_episodes: int = 5, deterministic: bool = True, max_steps: int = 6000):
+    """SB3 evaluate_policy on a (separate) vectorised env: mean / std of the first `n_eval_episodes` finished episodes."""
+    obs = torch.as_tensor(env.reset(), dtype=torch.float32, device=policy.log_std.device)
+    returns, lengths = [], []
+    first_done = torch.zeros(env.num_envs, dtype=torch.bool, device=obs.device)
+    for _ in range(max_steps + 1):
+        a, _, _ = policy.act(obs, deterministic=deterministic)
+        obs, rew, done, infos = env.step(a.clamp(-1.0, 1.0))
+        newly = done.to(torch.bool) & ~first_done
+        if bool(newly.any()):
+            returns += infos.episode_return[newly].tolist()
+            lengths += infos.episode_length[newly].tolist()
+            first_done |= newly
+        if len(returns) >= n_eval_episodes or bool(first_done.all()):
+            break
+    r = torch.tensor(returns[:max(1, n_eval_episodes)] or [float("nan")])
+    return float(r.mean()), float(r.std(unbiased=False)), lengths[:n_eval_episodes]
