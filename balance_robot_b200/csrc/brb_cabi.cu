@@ -107,7 +107,7 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
   e->S.qpos = TAKE(double);
   e->S.qvel = TAKE(double);
   e->S.xquat = TAKE(double);
-  e->S.warm = TAKE(float);
+  e->S.aset = TAKE(uint32_t);
   e->S.last_pitch = TAKE(double);
   e->S.ep_return = TAKE(double);
   e->S.v3 = TAKE(double);

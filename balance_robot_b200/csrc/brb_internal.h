@@ -20,7 +20,7 @@ struct BrbState {
   double *qpos;           // [9][N]  x y z qw qx qy qz thL thR        (MuJoCo data.qpos)
   double *qvel;           // [8][N]  v_world(3) w_body(3) sL sR       (MuJoCo data.qvel)
   double *xquat;          // [4][N]  chassis quaternion as the task logic sees it (one substep stale, Q1)
-  float *warm;            // [8][N]  chassis-frame solver acceleration of the last substep (qacc_warmstart)
+  uint32_t *aset;         // [N]     converged contact-row active set of the last substep (the solver's warm start)
   double *last_pitch;     // [N]     RobotBaseEnv.last_pitch
   double *ep_return;      // [N]     Monitor running return
   double *v3;             // [3][N]  target_wheel_speed, delay_target_speed, pitch_offset (Env01-v3 only)

@@ -165,7 +165,8 @@ BRB_D void reset_env(const BrbState &S, long long i, const double u[16], float o
 #pragma unroll
   for (int k = 0; k < 9; k++) S.qpos[k * N + i] = qpos[k];
 #pragma unroll
-  for (int k = 0; k < 8; k++) { S.qvel[k * N + i] = 0.0; S.warm[k * N + i] = 0.f; }
+  for (int k = 0; k < 8; k++) S.qvel[k * N + i] = 0.0;
+  S.aset[i] = 0xFFFFu;
   double xq[4];
   double n = sqrt(qpos[3] * qpos[3] + qpos[4] * qpos[4] + qpos[5] * qpos[5] + qpos[6] * qpos[6]);
 #pragma unroll
@@ -190,15 +191,22 @@ BRB_D void reset_env(const BrbState &S, long long i, const double u[16], float o
 __device__ unsigned long long g_trip[8];   // debug: warp-trips, lane-trips, warp-trips with a solve, lanes solving
 #endif
 
+BRB_D float mg_n(const BrbModelConsts &c, float n) { return c.mass * c.grav * n; }
+
+// Coordinates of the 8x8 contact system: world-frame linear acceleration (MuJoCo's own dofs 0-2), WORLD-frame angular
+// acceleration alpha_w = R alpha_b, wheel accelerations.  In these coordinates the contact frame of the z-up floor
+// (n = z, t1 = y, t2 = -x) is a signed permutation, so S_c = Pi' W_c Pi costs nothing and the point map
+// P_c = [I | -[r_w]x | w_w] is sparse; the price is M' = blockdiag(R,R,I) M_b blockdiag(R,R,I)' (24 flops per substep).
 struct Phys {
   // ---- state carried across substeps
   KF p[3], q[4], th[2], v[3], w[3], s[2];   // world pos, quat (w,x,y,z), wheel angles, world lin vel, body ang vel, wheel speeds
-  float a[8];                               // chassis-frame solver acceleration (warm start for the next substep)
   float uhi[2], ulo[2];                     // clamped ctrl targets, split hi/lo
-  // ---- working set of the current substep (setup() .. finalize())
-  float Xb[3], Yb[3], Zb[3];                // rows of R = world x/y/z axes in the chassis frame (contact frame: n=Zb, t1=Yb, t2=-Xb)
-  float f[8];                               // smooth generalized force in the chassis frame
-  float cr[4][3], cy[4][3];                 // contact point (chassis frame) and yhat = B*vel + (Kimp*dist, 0, 0)
+  unsigned bits;                            // converged pyramid-row active set of the last substep (4 bits per contact slot)
+  // ---- working set of the current substep (phys_setup() .. phys_finalize())
+  float ex[3], ey[3], ez[3];                // columns of R = chassis x/y/z axes in the world frame
+  float f[8];                               // smooth force: world linear (3), world angular (3), wheels (2)
+  float fb[8];                              // the same in the chassis frame (free-flight path: a_b = M_b^-1 f_b)
+  float cr[4][3], cw[4][3], cy[4][3];       // per contact: r_w (from the chassis origin), wheel column w_w, yhat (n, t1, t2)
   unsigned valid;                           // bit ci: contact slot ci (2*wheel + rim end) is in contact
   bool clampL, clampR;                      // servo sits on its forcerange (A.9)
   unsigned n_contact, n_solve, n_nonconv, n_slots;
@@ -206,45 +214,49 @@ struct Phys {
 
 // ---- A.3 steps 2-7: kinematics, smooth forces, collision, reference accelerations
 template <int CI>
-BRB_D void contact_setup(const BrbModelConsts &c, Phys &P, float d0, float anx, float sa, float vy, float vz, float u0, float u1,
-                         float u2) {
+BRB_D void contact_setup(const BrbModelConsts &c, Phys &P, float d0, float anx, float sa, const float (&G)[3], const float (&A)[3],
+                         const float (&B2)[3], const float (&ww)[3]) {
   constexpr int k = CI >> 1, e = CI & 1;
   const float sg = k ? 1.f : -1.f;
   const float dist = e ? d0 + c.hl * anx : d0 - c.hl * anx;
   if (dist < 0.f) {
     P.valid |= 1u << CI;
     const float hd = 0.5f * dist;
-    const float rx = sg * c.ox + (e ? -sa : sa) * c.hl - P.Zb[0] * hd;
-    const float ry = vy - P.Zb[1] * hd;
-    const float rz = c.oz + vz - P.Zb[2] * hd;
-    const float w0 = P.w[0].s, w1 = P.w[1].s, w2 = P.w[2].s, sk = P.s[k].s;
-    // material-point velocity: u + w x r + s_k * sg * (0, -(rz-oz), ry)
-    const float px = u0 + w1 * rz - w2 * ry;
-    const float py = u1 + w2 * rx - w0 * rz - sk * sg * (rz - c.oz);
-    const float pz = u2 + w0 * ry - w1 * rx + sk * sg * ry;
+    const float cx = sg * c.ox + (e ? -sa : sa) * c.hl;
+    // r_w = R (off_k +- a*hl + v) - e_z dist/2 ; w_w = R [axis_k x (r_b - off_k)] = sg (A + hd B2)
+    const float rx = P.ex[0] * cx + G[0], ry = P.ex[1] * cx + G[1], rz = P.ex[2] * cx + G[2] - hd;
+    const float wx = sg * (A[0] + hd * B2[0]), wy = sg * (A[1] + hd * B2[1]), wz = sg * (A[2] + hd * B2[2]);
+    const float sk = P.s[k].s;
+    // material-point velocity in the world frame: v + w_w x r_w + s_k w_w
+    const float px = P.v[0].s + ww[1] * rz - ww[2] * ry + sk * wx;
+    const float py = P.v[1].s + ww[2] * rx - ww[0] * rz + sk * wy;
+    const float pz = P.v[2].s + ww[0] * ry - ww[1] * rx + sk * wz;
     P.cr[CI][0] = rx; P.cr[CI][1] = ry; P.cr[CI][2] = rz;
-    P.cy[CI][0] = c.Bdamp * (P.Zb[0] * px + P.Zb[1] * py + P.Zb[2] * pz) + c.Kimp * dist;
-    P.cy[CI][1] = c.Bdamp * (P.Yb[0] * px + P.Yb[1] * py + P.Yb[2] * pz);
-    P.cy[CI][2] = -c.Bdamp * (P.Xb[0] * px + P.Xb[1] * py + P.Xb[2] * pz);
+    P.cw[CI][0] = wx; P.cw[CI][1] = wy; P.cw[CI][2] = wz;
+    P.cy[CI][0] = c.Bdamp * pz + c.Kimp * dist;
+    P.cy[CI][1] = c.Bdamp * py;
+    P.cy[CI][2] = -c.Bdamp * px;
   }
 }
 
 BRB_D void phys_setup(const BrbModelConsts &c, Phys &P) {
   const float qw = P.q[0].s, qx = P.q[1].s, qy = P.q[2].s, qz = P.q[3].s;
   const float xx = qx * qx, yy = qy * qy, zz = qz * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz, wx = qw * qx, wy = qw * qy, wz = qw * qz;
-  P.Xb[0] = 1.f - 2.f * (yy + zz); P.Xb[1] = 2.f * (xy - wz); P.Xb[2] = 2.f * (xz + wy);
-  P.Yb[0] = 2.f * (xy + wz); P.Yb[1] = 1.f - 2.f * (xx + zz); P.Yb[2] = 2.f * (yz - wx);
-  P.Zb[0] = 2.f * (xz - wy); P.Zb[1] = 2.f * (yz + wx); P.Zb[2] = 1.f - 2.f * (xx + yy);
+  P.ex[0] = 1.f - 2.f * (yy + zz); P.ey[0] = 2.f * (xy - wz); P.ez[0] = 2.f * (xz + wy);
+  P.ex[1] = 2.f * (xy + wz); P.ey[1] = 1.f - 2.f * (xx + zz); P.ez[1] = 2.f * (yz - wx);
+  P.ex[2] = 2.f * (xz - wy); P.ey[2] = 2.f * (yz + wx); P.ez[2] = 1.f - 2.f * (xx + yy);
+  // world z axis in the chassis frame = third row of R
+  const float n0 = P.ex[2], n1 = P.ey[2], n2 = P.ez[2];
   const float w0 = P.w[0].s, w1 = P.w[1].s, w2 = P.w[2].s, sL = P.s[0].s, sR = P.s[1].s;
   {
     const float mg = c.mass * c.grav, gm = c.grav * c.mcz;
-    P.f[0] = -c.mcz * (w0 * w2) - mg * P.Zb[0];
-    P.f[1] = -c.mcz * (w1 * w2) - mg * P.Zb[1];
-    P.f[2] = c.mcz * (w0 * w0 + w1 * w1) - mg * P.Zb[2];
+    P.fb[0] = -c.mcz * (w0 * w2) - mg * n0;
+    P.fb[1] = -c.mcz * (w1 * w2) - mg * n1;
+    P.fb[2] = c.mcz * (w0 * w0 + w1 * w1) - mg * n2;
     const float Lx = c.Ixx * w0 + c.Ia * (sR - sL), Ly = c.Iyy * w1, Lz = c.Izz * w2;
-    P.f[3] = -(w1 * Lz - w2 * Ly) + gm * P.Zb[1];
-    P.f[4] = -(w2 * Lx - w0 * Lz) - gm * P.Zb[0];
-    P.f[5] = -(w0 * Ly - w1 * Lx);
+    P.fb[3] = -(w1 * Lz - w2 * Ly) + gm * n1;
+    P.fb[4] = -(w2 * Lx - w0 * Lz) - gm * n0;
+    P.fb[5] = -(w0 * Ly - w1 * Lx);
     // servo: force = clip(kv (u - s), forcerange); u - s evaluated with the hi/lo halves (Q7)
     const float dL = (P.uhi[0] - sL) + (P.ulo[0] + P.s[0].c), dR = (P.uhi[1] - sR) + (P.ulo[1] + P.s[1].c);
     float tL = c.kv * dL, tR = c.kv * dR;
@@ -252,88 +264,91 @@ BRB_D void phys_setup(const BrbModelConsts &c, Phys &P) {
     P.clampR = (tR <= c.frc_lo) || (tR >= c.frc_hi);
     tL = fminf(c.frc_hi, fmaxf(c.frc_lo, tL));
     tR = fminf(c.frc_hi, fmaxf(c.frc_lo, tR));
-    P.f[6] = tL - c.damping * sL;
-    P.f[7] = tR - c.damping * sR;
+    P.fb[6] = tL - c.damping * sL;
+    P.fb[7] = tR - c.damping * sR;
   }
-  // plane-cylinder collision in the chassis frame (A.6): both rim ends of both wheels
+  // plane-cylinder collision (A.6), distances evaluated in the chassis frame: both rim ends of both wheels
   P.valid = 0;
-  const float rho2 = P.Zb[1] * P.Zb[1] + P.Zb[2] * P.Zb[2];
+  const float rho2 = n1 * n1 + n2 * n2;
   const float irho = rsqrtf(fmaxf(rho2, 1e-30f));
   const float rho = rho2 * irho;
   // oz*nz - rad*rho without cancellation when upright: (oz-rad) nz + rad (nz - rho), nz - rho = -ny^2/(nz+rho)
-  const float diff = (P.Zb[2] > 0.f) ? -(P.Zb[1] * P.Zb[1]) / (P.Zb[2] + rho) : (P.Zb[2] - rho);
+  const float diff = (n2 > 0.f) ? -(n1 * n1) / (n2 + rho) : (n2 - rho);
   const float hgt = ((P.p[2].s - c.zfloor) - P.p[2].c) - c.zfloor_lo;
-  const float common = hgt + (c.oz - c.rad) * P.Zb[2] + c.rad * diff;
-  const float anx = fabsf(P.Zb[0]);
+  const float common = hgt + (c.oz - c.rad) * n2 + c.rad * diff;
+  const float anx = fabsf(n0);
   const float dmin = common - c.ox * anx - c.hl * anx;          // lowest rim point of either wheel
   if (dmin < 0.f) {
-    const float vy = -c.rad * P.Zb[1] * irho, vz = -c.rad * P.Zb[2] * irho;
-    const float sa = (P.Zb[0] > 0.f) ? -1.f : 1.f;
-    const float u0 = P.v[0].s * P.Xb[0] + P.v[1].s * P.Yb[0] + P.v[2].s * P.Zb[0];   // chassis-frame linear velocity
-    const float u1 = P.v[0].s * P.Xb[1] + P.v[1].s * P.Yb[1] + P.v[2].s * P.Zb[1];
-    const float u2 = P.v[0].s * P.Xb[2] + P.v[1].s * P.Yb[2] + P.v[2].s * P.Zb[2];
-    const float dL0 = common - c.ox * P.Zb[0], dR0 = common + c.ox * P.Zb[0];
-    contact_setup<0>(c, P, dL0, anx, sa, vy, vz, u0, u1, u2);
-    contact_setup<1>(c, P, dL0, anx, sa, vy, vz, u0, u1, u2);
-    contact_setup<2>(c, P, dR0, anx, sa, vy, vz, u0, u1, u2);
-    contact_setup<3>(c, P, dR0, anx, sa, vy, vz, u0, u1, u2);
+    // world-frame copies of what the contact rows need
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      P.f[k] = P.ex[k] * (P.fb[0] + mg_n(c, n0)) + P.ey[k] * (P.fb[1] + mg_n(c, n1)) + P.ez[k] * (P.fb[2] + mg_n(c, n2));
+      P.f[3 + k] = P.ex[k] * P.fb[3] + P.ey[k] * P.fb[4] + P.ez[k] * P.fb[5];
+    }
+    P.f[2] -= c.mass * c.grav;                                   // R (-m g n_b) = -m g e_z exactly
+    P.f[6] = P.fb[6]; P.f[7] = P.fb[7];
+    const float vy = -c.rad * n1 * irho, vz = -c.rad * n2 * irho;   // rim direction toward the floor, chassis frame: (0, vy, vz)
+    const float sa = (n0 > 0.f) ? -1.f : 1.f;
+    float G[3], A[3], B2[3], ww[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++) {
+      G[k] = P.ey[k] * vy + P.ez[k] * (c.oz + vz);               // R (0, vy, oz + vz)
+      A[k] = P.ez[k] * vy - P.ey[k] * vz;                        // R (0, -vz, vy)
+      B2[k] = P.ey[k] * n2 - P.ez[k] * n1;                       // R (0, nz, -ny)
+      ww[k] = P.ex[k] * w0 + P.ey[k] * w1 + P.ez[k] * w2;        // world angular velocity
+    }
+    const float dL0 = common - c.ox * n0, dR0 = common + c.ox * n0;
+    contact_setup<0>(c, P, dL0, anx, sa, G, A, B2, ww);
+    contact_setup<1>(c, P, dL0, anx, sa, G, A, B2, ww);
+    contact_setup<2>(c, P, dR0, anx, sa, G, A, B2, ww);
+    contact_setup<3>(c, P, dR0, anx, sa, G, A, B2, ww);
   }
   if (P.valid) { P.n_contact++; P.n_slots += __popc(P.valid); }
 }
 
-// ---- active set at acceleration a: z_c = B (P_c a) + yhat_c, pyramid rows E_r . z_c < 0 (A.7, A.8).
+// ---- active set at acceleration a (world coordinates): z_c = Pi (P_c a) + yhat_c, pyramid rows E_r . z_c < 0 (A.7, A.8).
 // Rows within `eps` of the switching surface keep their previous state (`prev`): either choice gives the same
 // force to O(D*eps) ~ 2e-5 N, and without the hysteresis fp32 noise can flip such a row back and forth forever.
 template <int CI>
-BRB_D unsigned contact_bits(const BrbModelConsts &c, const Phys &P, unsigned prev) {
+BRB_D unsigned contact_bits(const BrbModelConsts &c, const Phys &P, const float (&a)[8], unsigned prev) {
   if (!(P.valid & (1u << CI))) return 0u;
-  constexpr int k = CI >> 1;
-  const float sg = k ? 1.f : -1.f;
-  const float ak = P.a[6 + k];
+  const float ak = a[6 + (CI >> 1)];
   const float rx = P.cr[CI][0], ry = P.cr[CI][1], rz = P.cr[CI][2];
-  const float px = P.a[0] + P.a[4] * rz - P.a[5] * ry;
-  const float py = P.a[1] + P.a[5] * rx - P.a[3] * rz - ak * sg * (rz - c.oz);
-  const float pz = P.a[2] + P.a[3] * ry - P.a[4] * rx + ak * sg * ry;
-  const float z0 = P.Zb[0] * px + P.Zb[1] * py + P.Zb[2] * pz + P.cy[CI][0];
-  const float z1 = c.mu * (P.Yb[0] * px + P.Yb[1] * py + P.Yb[2] * pz + P.cy[CI][1]);
-  const float z2 = c.mu * (P.cy[CI][2] - (P.Xb[0] * px + P.Xb[1] * py + P.Xb[2] * pz));
+  const float px = a[0] + a[4] * rz - a[5] * ry + ak * P.cw[CI][0];
+  const float py = a[1] + a[5] * rx - a[3] * rz + ak * P.cw[CI][1];
+  const float pz = a[2] + a[3] * ry - a[4] * rx + ak * P.cw[CI][2];
+  const float z0 = pz + P.cy[CI][0];
+  const float z1 = c.mu * (py + P.cy[CI][1]);
+  const float z2 = c.mu * (P.cy[CI][2] - px);
   const float eps = 2e-4f;
   const unsigned pb = prev >> (4 * CI);
   const float e0 = (pb & 1u) ? eps : -eps, e1 = (pb & 2u) ? eps : -eps, e2 = (pb & 4u) ? eps : -eps, e3 = (pb & 8u) ? eps : -eps;
   return ((unsigned)(z0 + z1 < e0) | ((unsigned)(z0 - z1 < e1) << 1) | ((unsigned)(z0 + z2 < e2) << 2) | ((unsigned)(z0 - z2 < e3) << 3)) << (4 * CI);
 }
 
-BRB_D unsigned phys_active_set(const BrbModelConsts &c, const Phys &P, unsigned prev) {
-  return contact_bits<0>(c, P, prev) | contact_bits<1>(c, P, prev) | contact_bits<2>(c, P, prev) | contact_bits<3>(c, P, prev);
+BRB_D unsigned phys_active_set(const BrbModelConsts &c, const Phys &P, const float (&a)[8], unsigned prev) {
+  return contact_bits<0>(c, P, a, prev) | contact_bits<1>(c, P, a, prev) | contact_bits<2>(c, P, a, prev) | contact_bits<3>(c, P, a, prev);
 }
 
-// ---- H += P_c' S_c P_c, r -= P_c' B' W_c yhat_c for one contact, S_c = B' W_c B
+// ---- H += P_c' S P_c, r -= P_c' S yhat-ish for one contact; S = Pi' W_c Pi in world axes:
+//      Sxx = W22, Syy = W11, Szz = W00, Syz = W01, Sxz = -W02, Sxy = 0
 template <int CI>
 BRB_D void contact_assemble(const BrbModelConsts &c, const Phys &P, unsigned bits, float (&H)[36], float (&r)[8]) {
   const unsigned b = (bits >> (4 * CI)) & 15u;
   if ((P.valid & (1u << CI)) && b) {
     constexpr int kw = 6 + (CI >> 1);
-    const float sg = (CI >> 1) ? 1.f : -1.f;
     const float b0 = (float)(b & 1u), b1 = (float)((b >> 1) & 1u), b2 = (float)((b >> 2) & 1u), b3 = (float)((b >> 3) & 1u);
     const float Dm = c.D * c.mu, Dmm = Dm * c.mu;
-    const float W00 = c.D * (b0 + b1 + b2 + b3), W01 = Dm * (b0 - b1), W02 = Dm * (b2 - b3);
-    const float W11 = Dmm * (b0 + b1), W22 = Dmm * (b2 + b3);
-    const float *X = P.Xb, *Y = P.Yb, *Z = P.Zb;
-    // rows of W B with B = [Zb; Yb; -Xb]
-    const float g00 = W00 * Z[0] + W01 * Y[0] - W02 * X[0], g01 = W00 * Z[1] + W01 * Y[1] - W02 * X[1], g02 = W00 * Z[2] + W01 * Y[2] - W02 * X[2];
-    const float g10 = W01 * Z[0] + W11 * Y[0], g11 = W01 * Z[1] + W11 * Y[1], g12 = W01 * Z[2] + W11 * Y[2];
-    const float g20 = W02 * Z[0] - W22 * X[0], g21 = W02 * Z[1] - W22 * X[1], g22 = W02 * Z[2] - W22 * X[2];
-    const float S00 = Z[0] * g00 + Y[0] * g10 - X[0] * g20, S01 = Z[0] * g01 + Y[0] * g11 - X[0] * g21, S02 = Z[0] * g02 + Y[0] * g12 - X[0] * g22;
-    const float S11 = Z[1] * g01 + Y[1] * g11 - X[1] * g21, S12 = Z[1] * g02 + Y[1] * g12 - X[1] * g22;
-    const float S22 = Z[2] * g02 + Y[2] * g12 - X[2] * g22;
+    const float Szz = c.D * (b0 + b1 + b2 + b3), Syz = Dm * (b0 - b1), Sxz = -Dm * (b2 - b3);
+    const float Syy = Dmm * (b0 + b1), Sxx = Dmm * (b2 + b3);
     const float rx = P.cr[CI][0], ry = P.cr[CI][1], rz = P.cr[CI][2];
-    const float wy_ = -sg * (rz - c.oz), wz_ = sg * ry;
-    // columns of P: e_x e_y e_z | cx=(0,-rz,ry) cy=(rz,0,-rx) cz=(-ry,rx,0) | w=(0,wy_,wz_);  T_j = S p_j
-    const float T3x = -rz * S01 + ry * S02, T3y = -rz * S11 + ry * S12, T3z = -rz * S12 + ry * S22;
-    const float T4x = rz * S00 - rx * S02, T4y = rz * S01 - rx * S12, T4z = rz * S02 - rx * S22;
-    const float T5x = -ry * S00 + rx * S01, T5y = -ry * S01 + rx * S11, T5z = -ry * S02 + rx * S12;
-    const float Twx = wy_ * S01 + wz_ * S02, Twy = wy_ * S11 + wz_ * S12, Twz = wy_ * S12 + wz_ * S22;
-    H[LT(0, 0)] += S00; H[LT(1, 0)] += S01; H[LT(2, 0)] += S02; H[LT(1, 1)] += S11; H[LT(2, 1)] += S12; H[LT(2, 2)] += S22;
+    const float wx = P.cw[CI][0], wy = P.cw[CI][1], wz = P.cw[CI][2];
+    // columns of P: e_x e_y e_z | cx=(0,-rz,ry) cy=(rz,0,-rx) cz=(-ry,rx,0) | w ;  T_j = S p_j
+    const float T3x = Sxz * ry, T3y = -Syy * rz + Syz * ry, T3z = -Syz * rz + Szz * ry;
+    const float T4x = Sxx * rz - Sxz * rx, T4y = -Syz * rx, T4z = Sxz * rz - Szz * rx;
+    const float T5x = -Sxx * ry, T5y = Syy * rx, T5z = -Sxz * ry + Syz * rx;
+    const float Twx = Sxx * wx + Sxz * wz, Twy = Syy * wy + Syz * wz, Twz = Sxz * wx + Syz * wy + Szz * wz;
+    H[LT(0, 0)] += Sxx; H[LT(2, 0)] += Sxz; H[LT(1, 1)] += Syy; H[LT(2, 1)] += Syz; H[LT(2, 2)] += Szz;
     H[LT(3, 0)] += T3x; H[LT(3, 1)] += T3y; H[LT(3, 2)] += T3z;
     H[LT(4, 0)] += T4x; H[LT(4, 1)] += T4y; H[LT(4, 2)] += T4z;
     H[LT(5, 0)] += T5x; H[LT(5, 1)] += T5y; H[LT(5, 2)] += T5z;
@@ -347,28 +362,43 @@ BRB_D void contact_assemble(const BrbModelConsts &c, const Phys &P, unsigned bit
     H[LT(kw, 3)] += -rz * Twy + ry * Twz;
     H[LT(kw, 4)] += rz * Twx - rx * Twz;
     H[LT(kw, 5)] += -ry * Twx + rx * Twy;
-    H[LT(kw, kw)] += wy_ * Twy + wz_ * Twz;
-    // rhs: g = -B' (W yhat)
+    H[LT(kw, kw)] += wx * Twx + wy * Twy + wz * Twz;
+    // rhs: g = -S yhat_w with yhat_w = (-y2, y1, y0) the contact-frame vector in world axes
     const float y0 = P.cy[CI][0], y1 = P.cy[CI][1], y2 = P.cy[CI][2];
-    const float t0 = W00 * y0 + W01 * y1 + W02 * y2, t1 = W01 * y0 + W11 * y1, t2 = W02 * y0 + W22 * y2;
-    const float gx = -(t0 * Z[0] + t1 * Y[0] - t2 * X[0]), gy = -(t0 * Z[1] + t1 * Y[1] - t2 * X[1]), gz = -(t0 * Z[2] + t1 * Y[2] - t2 * X[2]);
+    const float gx = Sxx * y2 - Sxz * y0, gy = -(Syy * y1 + Syz * y0), gz = Sxz * y2 - Syz * y1 - Szz * y0;
     r[0] += gx; r[1] += gy; r[2] += gz;
     r[3] += -rz * gy + ry * gz;
     r[4] += rz * gx - rx * gz;
     r[5] += -ry * gx + rx * gy;
-    r[kw] += wy_ * gy + wz_ * gz;
+    r[kw] += wx * gx + wy * gy + wz * gz;
   }
 }
 
-// ---- one Newton step on the active set `bits`: (M_b + sum P'SP) a = f - sum P'B'W yhat   (A.8; exact for a fixed set)
-BRB_D void phys_solve(const BrbModelConsts &c, Phys &P, unsigned bits) {
+// ---- one Newton step on the active set `bits`: (M' + sum P'SP) a = f - sum P'S yhat   (A.8; exact for a fixed set)
+BRB_D void phys_solve(const BrbModelConsts &c, Phys &P, unsigned bits, float (&a)[8]) {
   float H[36], r[8];
 #pragma unroll
   for (int k = 0; k < 36; k++) H[k] = 0.f;
+  // M' = blockdiag(R, R, I) M_b blockdiag(R, R, I)'
   H[LT(0, 0)] = c.mass; H[LT(1, 1)] = c.mass; H[LT(2, 2)] = c.mass;
-  H[LT(4, 0)] = c.mcz; H[LT(3, 1)] = -c.mcz;
-  H[LT(3, 3)] = c.Ixx; H[LT(4, 4)] = c.Iyy; H[LT(5, 5)] = c.Izz;
-  H[LT(6, 3)] = -c.Ia; H[LT(7, 3)] = c.Ia; H[LT(6, 6)] = c.Ia; H[LT(7, 7)] = c.Ia;
+  {
+    const float kx = c.mcz * P.ez[0], ky = c.mcz * P.ez[1], kz = c.mcz * P.ez[2];   // M_la = -m [c_w]x, c_w = cz ez
+    H[LT(4, 0)] = kz;  H[LT(5, 0)] = -ky;
+    H[LT(3, 1)] = -kz; H[LT(5, 1)] = kx;
+    H[LT(3, 2)] = ky;  H[LT(4, 2)] = -kx;
+    const float dx = c.Ixx - c.Iyy, dz = c.Izz - c.Iyy;                              // R I_O R' = Iyy 1 + dx ex ex' + dz ez ez'
+    const float ax = dx * P.ex[0], ay = dx * P.ex[1], az = dx * P.ex[2], bx = dz * P.ez[0], by = dz * P.ez[1], bz = dz * P.ez[2];
+    H[LT(3, 3)] = c.Iyy + ax * P.ex[0] + bx * P.ez[0];
+    H[LT(4, 3)] = ay * P.ex[0] + by * P.ez[0];
+    H[LT(5, 3)] = az * P.ex[0] + bz * P.ez[0];
+    H[LT(4, 4)] = c.Iyy + ay * P.ex[1] + by * P.ez[1];
+    H[LT(5, 4)] = az * P.ex[1] + bz * P.ez[1];
+    H[LT(5, 5)] = c.Iyy + az * P.ex[2] + bz * P.ez[2];
+    const float hx = c.Ia * P.ex[0], hy = c.Ia * P.ex[1], hz = c.Ia * P.ex[2];       // wheel axes -+ex
+    H[LT(6, 3)] = -hx; H[LT(6, 4)] = -hy; H[LT(6, 5)] = -hz;
+    H[LT(7, 3)] = hx;  H[LT(7, 4)] = hy;  H[LT(7, 5)] = hz;
+    H[LT(6, 6)] = c.Ia; H[LT(7, 7)] = c.Ia;
+  }
 #pragma unroll
   for (int k = 0; k < 8; k++) r[k] = P.f[k];
   contact_assemble<0>(c, P, bits, H, r);
@@ -378,45 +408,30 @@ BRB_D void phys_solve(const BrbModelConsts &c, Phys &P, unsigned bits) {
   // Cholesky H = L L' and the two triangular solves, straight-line (generated: gen_chol8.py)
 #include "brb_chol8.inc"
 #pragma unroll
-  for (int k = 0; k < 8; k++) P.a[k] = r[k];
+  for (int k = 0; k < 8; k++) a[k] = r[k];
   P.n_solve++;
 }
 
-// ---- free flight: a = M_b^-1 f
-BRB_D void phys_free_accel(const BrbModelConsts &c, Phys &P) {
-  const float *f = P.f;
-  P.a[0] = c.minv_xy[0] * f[0] + c.minv_xy[1] * f[4];
-  P.a[4] = c.minv_xy[1] * f[0] + c.minv_xy[2] * f[4];
-  P.a[2] = c.minv_uz * f[2];
-  P.a[5] = c.minv_wz * f[5];
-  P.a[1] = c.minv_blk[0] * f[1] + c.minv_blk[1] * f[3] + c.minv_blk[2] * f[6] + c.minv_blk[3] * f[7];
-  P.a[3] = c.minv_blk[1] * f[1] + c.minv_blk[4] * f[3] + c.minv_blk[5] * f[6] + c.minv_blk[6] * f[7];
-  P.a[6] = c.minv_blk[2] * f[1] + c.minv_blk[5] * f[3] + c.minv_blk[7] * f[6] + c.minv_blk[8] * f[7];
-  P.a[7] = c.minv_blk[3] * f[1] + c.minv_blk[6] * f[3] + c.minv_blk[8] * f[6] + c.minv_blk[9] * f[7];
-}
-
-// ---- A.9 + A.10: implicitfast velocity update, then positions with the NEW velocities.  P.a keeps the
-// solver's acceleration (MuJoCo's qacc / qacc_warmstart), the implicit correction is applied to a copy.
-BRB_D void phys_finalize(const BrbModelConsts &c, Phys &P) {
-  float a1 = P.a[1], a3 = P.a[3], a6 = P.a[6], a7 = P.a[7];
+// ---- A.9 + A.10: implicitfast velocity update, then positions with the NEW velocities.
+// av = world linear acceleration, ab = chassis-frame angular acceleration, a6/a7 = wheels: the SOLVER's acceleration.
+BRB_D void phys_finalize(const BrbModelConsts &c, Phys &P, float avx, float avy, float avz, float ab0, float ab1, float ab2, float a6, float a7) {
   {
-    // a+ = (M + h Dv)^-1 M a = a - Wm (Cinv + G)^-1 [a6; a7]   (Woodbury on the two wheel dofs)
+    // a+ = (M + h Dv)^-1 M a = a - Wm (Cinv + G)^-1 [a6; a7]   (Woodbury on the two wheel dofs; Wm touches uy, wx, sL, sR)
     const bool skip = (c.flags & BRB_FLAG_ACTDERIV_SKIP_CLAMPED) != 0;
     const float cL = (skip && P.clampL) ? c.impl_cinv_damp : c.impl_cinv_full;
     const float cR = (skip && P.clampR) ? c.impl_cinv_damp : c.impl_cinv_full;
     const float k00 = cL + c.impl_G[0], k01 = c.impl_G[1], k11 = cR + c.impl_G[2];
     const float idet = 1.f / (k00 * k11 - k01 * k01);
     const float y0 = (k11 * a6 - k01 * a7) * idet, y1 = (k00 * a7 - k01 * a6) * idet;
-    a1 -= c.impl_W[0] * y0 + c.impl_W[1] * y1;
-    a3 -= c.impl_W[2] * y0 + c.impl_W[3] * y1;
+    const float duy = c.impl_W[0] * y0 + c.impl_W[1] * y1;      // chassis-frame y component of the linear correction
+    avx -= P.ey[0] * duy; avy -= P.ey[1] * duy; avz -= P.ey[2] * duy;
+    ab0 -= c.impl_W[2] * y0 + c.impl_W[3] * y1;
     a6 -= c.impl_W[4] * y0 + c.impl_W[5] * y1;
     a7 -= c.impl_W[6] * y0 + c.impl_W[7] * y1;
   }
-  const float h = c.h, a0 = P.a[0], a2 = P.a[2];
-  kadd(P.v[0], h * (P.Xb[0] * a0 + P.Xb[1] * a1 + P.Xb[2] * a2));
-  kadd(P.v[1], h * (P.Yb[0] * a0 + P.Yb[1] * a1 + P.Yb[2] * a2));
-  kadd(P.v[2], h * (P.Zb[0] * a0 + P.Zb[1] * a1 + P.Zb[2] * a2));
-  kadd(P.w[0], h * a3); kadd(P.w[1], h * P.a[4]); kadd(P.w[2], h * P.a[5]);
+  const float h = c.h;
+  kadd(P.v[0], h * avx); kadd(P.v[1], h * avy); kadd(P.v[2], h * avz);
+  kadd(P.w[0], h * ab0); kadd(P.w[1], h * ab1); kadd(P.w[2], h * ab2);
   kadd(P.s[0], h * a6); kadd(P.s[1], h * a7);
   kadd(P.p[0], h * P.v[0].s - h * P.v[0].c);
   kadd(P.p[1], h * P.v[1].s - h * P.v[1].c);
@@ -446,10 +461,10 @@ BRB_D void phys_run(const BrbModelConsts &c, Phys &P, int nsub, KF (&qstale)[4])
   int sidx = 0, it = 0;
   // The active set of a new substep is seeded with the previous substep's converged set (rows of a contact that just
   // appeared start "all active"): right ~97 % of the time, and the post-solve check below catches the rest.
-  unsigned bits = 0xFFFFu;
   phys_setup(c, P);
   for (;;) {
     bool conv = true;
+    float avx, avy, avz, ab0, ab1, ab2, a6, a7;
 #ifdef BRB_TRIPSTATS
     {
       const unsigned act = __activemask();
@@ -461,27 +476,45 @@ BRB_D void phys_run(const BrbModelConsts &c, Phys &P, int nsub, KF (&qstale)[4])
     }
 #endif
     if (P.valid) {
-      phys_solve(c, P, bits);
-      const unsigned nb = phys_active_set(c, P, bits);
-      conv = (nb == bits);
-      bits = nb;
+      float a[8];
+      phys_solve(c, P, P.bits, a);
+      const unsigned nb = phys_active_set(c, P, a, P.bits);
+      conv = (nb == P.bits);
+      P.bits = nb;
       if (!conv && ++it >= MAXIT) { P.n_nonconv++; conv = true; }
+      avx = a[0]; avy = a[1]; avz = a[2];
+      ab0 = P.ex[0] * a[3] + P.ex[1] * a[4] + P.ex[2] * a[5];      // alpha_b = R' alpha_w
+      ab1 = P.ey[0] * a[3] + P.ey[1] * a[4] + P.ey[2] * a[5];
+      ab2 = P.ez[0] * a[3] + P.ez[1] * a[4] + P.ez[2] * a[5];
+      a6 = a[6]; a7 = a[7];
     } else {
-      phys_free_accel(c, P);
+      // free flight: a_b = M_b^-1 f_b in the chassis frame, linear part rotated to the world
+      const float *f = P.fb;
+      const float u0 = c.minv_xy[0] * f[0] + c.minv_xy[1] * f[4];
+      const float u1 = c.minv_blk[0] * f[1] + c.minv_blk[1] * f[3] + c.minv_blk[2] * f[6] + c.minv_blk[3] * f[7];
+      const float u2 = c.minv_uz * f[2];
+      avx = P.ex[0] * u0 + P.ey[0] * u1 + P.ez[0] * u2;
+      avy = P.ex[1] * u0 + P.ey[1] * u1 + P.ez[1] * u2;
+      avz = P.ex[2] * u0 + P.ey[2] * u1 + P.ez[2] * u2;
+      ab0 = c.minv_blk[1] * f[1] + c.minv_blk[4] * f[3] + c.minv_blk[5] * f[6] + c.minv_blk[6] * f[7];
+      ab1 = c.minv_xy[1] * f[0] + c.minv_xy[2] * f[4];
+      ab2 = c.minv_wz * f[5];
+      a6 = c.minv_blk[2] * f[1] + c.minv_blk[5] * f[3] + c.minv_blk[7] * f[6] + c.minv_blk[8] * f[7];
+      a7 = c.minv_blk[3] * f[1] + c.minv_blk[6] * f[3] + c.minv_blk[8] * f[6] + c.minv_blk[9] * f[7];
     }
     if (conv) {
       if (sidx == nsub - 1) {
 #pragma unroll
         for (int k = 0; k < 4; k++) qstale[k] = P.q[k];
       }
-      phys_finalize(c, P);
+      phys_finalize(c, P, avx, avy, avz, ab0, ab1, ab2, a6, a7);
       if (++sidx >= nsub) break;
       const unsigned was = P.valid;
       phys_setup(c, P);
       it = 0;
       // slots that were not in contact a substep ago start with all four pyramid rows active
       const unsigned fresh = P.valid & ~was;
-      bits |= ((fresh & 1u) ? 0xFu : 0u) | ((fresh & 2u) ? 0xF0u : 0u) | ((fresh & 4u) ? 0xF00u : 0u) | ((fresh & 8u) ? 0xF000u : 0u);
+      P.bits |= ((fresh & 1u) ? 0xFu : 0u) | ((fresh & 2u) ? 0xF0u : 0u) | ((fresh & 4u) ? 0xF00u : 0u) | ((fresh & 8u) ? 0xF000u : 0u);
     }
   }
 }
@@ -573,7 +606,7 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
       st.ulo[k] = (float)(u - (double)st.uhi[k]);
     }
 #pragma unroll
-    for (int k = 0; k < 8; k++) st.a[k] = S.warm[k * N + i];
+    st.bits = S.aset[i];
     st.n_contact = st.n_solve = st.n_nonconv = st.n_slots = 0;
   }
   const int nsub = c.frame_skip;
@@ -656,7 +689,8 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
 #pragma unroll
     for (int k = 0; k < 9; k++) S.qpos[k * N + i] = qpos[k];
 #pragma unroll
-    for (int k = 0; k < 8; k++) { S.qvel[k * N + i] = qvel[k]; S.warm[k * N + i] = st.a[k]; }
+    for (int k = 0; k < 8; k++) S.qvel[k * N + i] = qvel[k];
+    S.aset[i] = st.bits;
 #pragma unroll
     for (int k = 0; k < 4; k++) S.xquat[k * N + i] = xq[k];
     S.elapsed[i] = elapsed;
@@ -761,7 +795,8 @@ __global__ void brb_set_state_kernel(const BrbState S, const double *qpos, const
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S.n) return;
   for (int k = 0; k < 9; k++) S.qpos[k * S.n + i] = qpos[i * 9 + k];
-  for (int k = 0; k < 8; k++) { S.qvel[k * S.n + i] = qvel[i * 8 + k]; S.warm[k * S.n + i] = 0.f; }
+  for (int k = 0; k < 8; k++) S.qvel[k * S.n + i] = qvel[i * 8 + k];
+  S.aset[i] = 0xFFFFu;
   double nn = 0;
   for (int k = 0; k < 4; k++) nn += qpos[i * 9 + 3 + k] * qpos[i * 9 + 3 + k];
   nn = 1.0 / sqrt(nn);

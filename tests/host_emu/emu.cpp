@@ -19,14 +19,14 @@ extern "C" Emu *emu_create(const BrbModelConsts *c, const double *tt, int n_time
   BrbState &S = e->S;
   S.n = n; S.env0 = env0; S.seed = seed;
   S.qpos = (double *)calloc(9 * n, 8); S.qvel = (double *)calloc(8 * n, 8); S.xquat = (double *)calloc(4 * n, 8);
-  S.warm = (float *)calloc(8 * n, 4); S.last_pitch = (double *)calloc(n, 8); S.ep_return = (double *)calloc(n, 8);
+  S.aset = (uint32_t *)calloc(n, 4); S.last_pitch = (double *)calloc(n, 8); S.ep_return = (double *)calloc(n, 8);
   S.v3 = (double *)calloc(3 * n, 8); S.elapsed = (int *)calloc(n, 4); S.ep_len = (int *)calloc(n, 4);
   S.event = (uint32_t *)calloc(n, 4); S.time_table = e->tt; S.stats = e->stats;
   return e;
 }
 extern "C" void emu_destroy(Emu *e) {
   BrbState &S = e->S;
-  free(S.qpos); free(S.qvel); free(S.xquat); free(S.warm); free(S.last_pitch); free(S.ep_return); free(S.v3);
+  free(S.qpos); free(S.qvel); free(S.xquat); free(S.aset); free(S.last_pitch); free(S.ep_return); free(S.v3);
   free(S.elapsed); free(S.ep_len); free(S.event); free(e->tt); free(e);
 }
 template <int KIND> static void reset_all(Emu *e, float *obs, const double *replay) {
@@ -75,7 +75,8 @@ extern "C" void emu_set_state(Emu *e, const double *qpos, const double *qvel) {
   const long long n = e->S.n;
   for (long long i = 0; i < n; i++) {
     for (int k = 0; k < 9; k++) e->S.qpos[k * n + i] = qpos[i * 9 + k];
-    for (int k = 0; k < 8; k++) { e->S.qvel[k * n + i] = qvel[i * 8 + k]; e->S.warm[k * n + i] = 0.f; }
+    for (int k = 0; k < 8; k++) e->S.qvel[k * n + i] = qvel[i * 8 + k];
+    e->S.aset[i] = 0xFFFFu;
     double nn = 0;
     for (int k = 0; k < 4; k++) nn += qpos[i * 9 + 3 + k] * qpos[i * 9 + 3 + k];
     nn = 1.0 / sqrt(nn);
