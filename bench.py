@@ -34,6 +34,9 @@ FRAME_SKIP = 250
 ALG_FLOP_PER_ENV_STEP = FLOP_PER_SUBSTEP_CONTACT * FRAME_SKIP          # 9.25e5 ("9.3e5" in SURVEY.md)
 ALG_BYTES_PER_ENV_STEP = 290.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
+# dram__bytes_read.sum + dram__bytes_write.sum of brb_step_kernel<1> from the committed `ncu --set full` capture
+# (profiles/r1_step_kernel_ncu_raw.csv: 15,561,984 + 14,592 bytes for 65,536 robots) -> bytes per robot-step
+NCU_DRAM_BYTES_PER_ENV_STEP = (15561984 + 14592) / 65536
 
 
 def parse_args():
@@ -48,6 +51,8 @@ def parse_args():
     ap.add_argument("--cpu-threads", type=int, default=0, help="threads for the CPU legs (0 = all cores)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--actions", default="random", choices=["random", "policy"],
+                    help="random: U(-1,1)^2 resident in HBM (BASELINE configs[1]); policy: on-device MlpPolicy inference every step")
     return ap.parse_args()
 
 
@@ -55,7 +60,9 @@ def workload_config(args, world):
     return {"workload": f"{args.env} random-action rollout, {args.envs_per_gpu} envs per GPU x {world} GPU(s), "
                         "250 substeps/step (h=2e-5, implicitfast), auto-reset, Philox noise",
             "env": args.env, "envs_per_gpu": args.envs_per_gpu, "n_envs": args.envs_per_gpu * world,
-            "frame_skip": FRAME_SKIP, "actions": "U(-1,1)^2, torch.Generator(cuda).manual_seed(1234)",
+            "frame_skip": FRAME_SKIP,
+            "actions": "U(-1,1)^2, torch.Generator(cuda).manual_seed(1234)" if args.actions == "random"
+            else "on-device MlpPolicy (6-64-64-2 tanh, random init seed 0) sampled every step inside the timed region",
             "cache": "L2 flushed (256 MiB write) before every timed step", "sharding": f"env-dp{world}"}
 
 
@@ -169,8 +176,23 @@ def run_b200(args, rank, world, local_rank):
     _cabi.check(_cabi.lib().brb_fp32_peak_flops(local_rank, C.byref(fl), C.byref(ms)), "brb_fp32_peak_flops")
     fp32_peak = fl.value
 
+    policy = None
+    if args.actions == "policy":
+        from balance_robot_b200.ppo import MlpPolicy
+        torch.manual_seed(0)
+        policy = MlpPolicy().to(dev)
+    obs_t = env.reset()
+
+    def one_step(k):
+        nonlocal obs_t
+        if policy is None:
+            obs_t = env.step(acts[k % nact])[0]
+        else:
+            a, _, _ = policy.act(obs_t, generator=gen)
+            obs_t = env.step(a.clamp(-1.0, 1.0))[0]
+
     for k in range(args.warmup):
-        env.step(acts[k % nact])
+        one_step(k)
     torch.cuda.synchronize(dev)
     stats0 = env.stats()
     launches0 = env.num_launches()
@@ -183,7 +205,7 @@ def run_b200(args, rank, world, local_rank):
     for k in range(args.steps):
         flush.fill_(k & 0xFF)            # evict L2 (126 MB) between timed steps; not inside the event pair
         ev[k][0].record()
-        env.step(acts[k % nact])
+        one_step(k)
         ev[k][1].record()
     torch.cuda.synchronize(dev)
     if dist is not None:
@@ -250,7 +272,9 @@ def run_b200(args, rank, world, local_rank):
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
                 "frac": achieved / (fp32_peak / 1e12),
-                "traffic": None,
+                "traffic": NCU_DRAM_BYTES_PER_ENV_STEP * n,
+                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r1_step_kernel_ncu_raw.csv "
+                                  "(237 B per robot-step, scaled to this shard); algorithmic bytes = 290 B per robot-step",
                 "peak_source": "FFMA probe kernel measured in this run (brb_fp32_peak_flops); MEASURED_PEAKS.json has no FP32 entry; "
                                f"nominal {NOMINAL_FP32_TFLOPS:.1f}",
                 "algorithmic_flop_per_env_step": ALG_FLOP_PER_ENV_STEP,
