@@ -298,19 +298,23 @@ class PPO:
 
 @torch.no_grad()
 def evaluate_policy(policy: MlpPolicy, env, n_eval_episodes: int = 5, deterministic: bool = True, max_steps: int = 6000):
-    """SB3 evaluate_policy on a (separate) vectorised env: mean / std of the first `n_eval_episodes` finished episodes."""
+    """SB3 evaluate_policy on a (separate) vectorised env: mean / std of the FIRST episode of each of the first
+    `n_eval_episodes` envs.  (Taking the first episodes to finish anywhere in the batch would favour short ones —
+    12.8 % of Env01-v2 episodes end at their first step, SURVEY.md Q3 — which is why SB3 fixes a per-env quota too.)"""
+    n = min(n_eval_episodes, env.num_envs)
     obs = torch.as_tensor(env.reset(), dtype=torch.float32, device=policy.log_std.device)
-    returns, lengths = [], []
-    first_done = torch.zeros(env.num_envs, dtype=torch.bool, device=obs.device)
+    ret = torch.zeros(n, device=obs.device)
+    length = torch.zeros(n, device=obs.device)
+    finished = torch.zeros(n, dtype=torch.bool, device=obs.device)
     for _ in range(max_steps + 1):
         a, _, _ = policy.act(obs, deterministic=deterministic)
         obs, rew, done, infos = env.step(a.clamp(-1.0, 1.0))
-        newly = done.to(torch.bool) & ~first_done
+        newly = done[:n].to(torch.bool) & ~finished
         if bool(newly.any()):
-            returns += infos.episode_return[newly].tolist()
-            lengths += infos.episode_length[newly].tolist()
-            first_done |= newly
-        if len(returns) >= n_eval_episodes or bool(first_done.all()):
+            ret[newly] = infos.episode_return[:n][newly].to(ret.dtype)
+            length[newly] = infos.episode_length[:n][newly].to(length.dtype)
+            finished |= newly
+        if bool(finished.all()):
             break
-    r = torch.tensor(returns[:max(1, n_eval_episodes)] or [float("nan")])
-    return float(r.mean()), float(r.std(unbiased=False)), lengths[:n_eval_episodes]
+    r = ret[finished] if bool(finished.any()) else torch.tensor([float("nan")])
+    return float(r.mean()), float(r.std(unbiased=False)), [int(x) for x in length[finished].tolist()]

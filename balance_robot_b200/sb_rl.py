@@ -87,7 +87,7 @@ def train(ctx, environment, num_envs, total_timesteps, n_steps, device, seed):
             writer = SummaryWriter(str(pathlib.Path(LOG_DIR) / f"{environment}_{algo}_{k}"))     # tb_log_name, sb_rl.py:554
         except Exception as exc:  # tensorboard missing: keep training, say so
             logging.warning("tensorboard unavailable (%s); scalars go to stdout only", exc)
-    eval_env = make_vec(environment, 64, device=device, seed=seed + 7919) if rank == 0 else None
+    eval_env = make_vec(environment, 5, device=device, seed=seed + 7919) if rank == 0 else None     # n_eval_episodes=5, sb_rl.py:540
     per_iter = n_steps * num_envs * world
     state = {"best": -float("inf"), "next_eval": 20000, "next_ckpt": 40000, "no_improve": 0, "evals": 0}
 
