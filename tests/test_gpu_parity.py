@@ -212,3 +212,50 @@ def test_truncation_and_monitor_on_device(spec):
     live = (d == 0).cpu()
     assert torch.allclose(info.episode_return.cpu()[live].double(), total.cpu()[live], rtol=1e-5)
     env.close()
+
+
+def test_episode_statistics_agree_with_oracle(spec):
+    """north_star: episode returns must agree statistically.  Same stochastic policy (weak PD + uniform exploration noise), independent noise
+    streams: episode length / return distributions of the CUDA path (thousands of episodes) vs the fp64 oracle."""
+    from oracle import ref
+    rng = np.random.default_rng(0)
+
+    def run(step_fn, reset_fn, n, steps):
+        obs = reset_fn()
+        lens, rets = [], []
+        for t in range(steps):
+            act = np.clip(0.03 * helpers.pd_policy(obs) + rng.uniform(-1, 1, (n, 2)), -1, 1).astype(np.float32)   # weak, noisy policy: episodes of ~40 steps
+            obs, done, epr, epl = step_fn(act, t)
+            lens += epl[done].tolist()
+            rets += epr[done].tolist()
+        return np.array(lens), np.array(rets)
+
+    n_o, n_g, steps = 256, 8192, 200
+    rv = ref.RefVecEnv(spec, "Env01-v2", n_o, 6000, nthreads=8)
+
+    def o_reset():
+        return rv.reset(ref.philox_draws(77, 0, n_o, 0)[1])
+
+    def o_step(act, t):
+        us, ur = ref.philox_draws(77, 0, n_o, t + 1)
+        obs, rew, done, trunc = rv.step(act, us, ur)
+        return obs, done.astype(bool), rv.ep_return.copy(), rv.ep_len.copy()
+    lo, ro = run(o_step, o_reset, n_o, steps)
+    env = GpuAdapter("Env01-v2", n_g, 78)
+
+    def g_step(act, t):
+        obs, rew, done, trunc = env.step(act)
+        return obs, done.astype(bool), env.epr.copy(), env.epl.copy()
+    lg, rg = run(g_step, env.reset, n_g, steps)
+    assert len(lo) > 300 and len(lg) > 10000
+    # one-step episodes (Q3: ~12.8 % start beyond 50 degrees)
+    assert abs((lo == 1).mean() - (lg == 1).mean()) < 0.05
+    assert abs((lg == 1).mean() - 0.128) < 0.03
+    # means within 4 standard errors of the (smaller) oracle sample
+    for a, b in ((lo, lg), (ro, rg)):
+        se = a.std() / np.sqrt(len(a)) + b.std() / np.sqrt(len(b))
+        assert abs(a.mean() - b.mean()) < 4 * se + 1e-9, (a.mean(), b.mean(), se)
+    # quartiles of the episode-length distribution
+    qo, qg = np.quantile(lo, [0.25, 0.5, 0.75]), np.quantile(lg, [0.25, 0.5, 0.75])
+    assert np.all(np.abs(qo - qg) <= np.maximum(3, 0.25 * qg)), (qo, qg)
+    env.close(); rv.close()
