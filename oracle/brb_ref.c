@@ -396,6 +396,117 @@ static void collide_plane_box(const BrbRefModel *m, BrbRefData *d, int pair) {
   }
 }
 
+
+/* box-box: separating-axis test over the 15 candidate axes, then either face clipping (reference face = axis of least
+ * penetration, incident face of the other box clipped against its side planes, Sutherland-Hodgman) or the closest points
+ * of the two edges.  NOT a restatement of MuJoCo's mjc_BoxBox (engine_collision_box.c, several hundred lines that are not
+ * reproducible from memory): it yields the same contact manifold class (<= 8 points, normal = axis of least penetration,
+ * point = midway between the surfaces) but individual points can differ.  Contact normal points from geom1 to geom2. */
+static void collide_box_box(const BrbRefModel *m, BrbRefData *d, int pair) {
+  int g1 = m->pair_geom1[pair], g2 = m->pair_geom2[pair];
+  const double *R1 = d->geom_xmat[g1], *R2 = d->geom_xmat[g2], *p1 = d->geom_xpos[g1], *p2 = d->geom_xpos[g2];
+  const double *h1 = m->geom_size[g1], *h2 = m->geom_size[g2];
+  double margin = m->pair_margin[pair];
+  double dp[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  double A[3][3], B[3][3]; /* box axes (columns of R) as rows here */
+  for (int i = 0; i < 3; i++)
+    for (int k = 0; k < 3; k++) { A[i][k] = R1[3 * k + i]; B[i][k] = R2[3 * k + i]; }
+  double best = -1e30, bestn[3] = {0, 0, 1};
+  int bestkind = -1, bi = 0, bj = 0; /* kind 0: face of 1, 1: face of 2, 2: edge-edge */
+  for (int kind = 0; kind < 2; kind++)
+    for (int i = 0; i < 3; i++) {
+      const double *L = kind == 0 ? A[i] : B[i];
+      double r1 = 0, r2 = 0;
+      for (int k = 0; k < 3; k++) { r1 += h1[k] * fabs(dot3(A[k], L)); r2 += h2[k] * fabs(dot3(B[k], L)); }
+      double t = dot3(dp, L), s = fabs(t) - (r1 + r2);
+      if (s > margin) return;
+      if (s > best) {
+        best = s; bestkind = kind; bi = i;
+        for (int k = 0; k < 3; k++) bestn[k] = t >= 0 ? L[k] : -L[k];
+      }
+    }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      double L[3];
+      cross3(L, A[i], B[j]);
+      double n = sqrt(dot3(L, L));
+      if (n < 1e-6) continue;
+      for (int k = 0; k < 3; k++) L[k] /= n;
+      double r1 = 0, r2 = 0;
+      for (int k = 0; k < 3; k++) { r1 += h1[k] * fabs(dot3(A[k], L)); r2 += h2[k] * fabs(dot3(B[k], L)); }
+      double t = dot3(dp, L), s = fabs(t) - (r1 + r2);
+      if (s > margin) return;
+      if (s > best + 1e-3 * fabs(best) + 1e-9 && s > 0.95 * best + (best < 0 ? 0.05 * best : 0) ) {
+        /* edge axes win only when clearly better than the best face axis (standard bias towards face contacts) */
+        if (s > best + 1e-4) { best = s; bestkind = 2; bi = i; bj = j; for (int k = 0; k < 3; k++) bestn[k] = t >= 0 ? L[k] : -L[k]; }
+      }
+    }
+  if (bestkind == 2) {
+    /* closest points of edge bi of box 1 and edge bj of box 2: pick the edges supporting along +-n */
+    double c1[3], c2[3];
+    for (int k = 0; k < 3; k++) { c1[k] = p1[k]; c2[k] = p2[k]; }
+    for (int a = 0; a < 3; a++) {
+      if (a != bi) { double sg = dot3(A[a], bestn) > 0 ? 1 : -1; for (int k = 0; k < 3; k++) c1[k] += sg * h1[a] * A[a][k]; }
+      if (a != bj) { double sg = dot3(B[a], bestn) > 0 ? -1 : 1; for (int k = 0; k < 3; k++) c2[k] += sg * h2[a] * B[a][k]; }
+    }
+    const double *u = A[bi], *v = B[bj];
+    double w[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
+    double uv = dot3(u, v), uw = dot3(u, w), vw = dot3(v, w), den = 1 - uv * uv;
+    double sa = den > 1e-12 ? (uv * vw - uw) / den : 0, sb = den > 1e-12 ? (vw - uv * uw) / den : 0;
+    sa = fmax(-h1[bi], fmin(h1[bi], sa)); sb = fmax(-h2[bj], fmin(h2[bj], sb));
+    double q1[3], q2[3], pos[3];
+    for (int k = 0; k < 3; k++) { q1[k] = c1[k] + sa * u[k]; q2[k] = c2[k] + sb * v[k]; pos[k] = 0.5 * (q1[k] + q2[k]); }
+    new_contact(d, m, pair, best, pos, bestn);
+    return;
+  }
+  /* face contact: reference box/face, incident box */
+  const double (*RA)[3] = bestkind == 0 ? A : B, (*IB)[3] = bestkind == 0 ? B : A;
+  const double *hr = bestkind == 0 ? h1 : h2, *hi = bestkind == 0 ? h2 : h1, *pr = bestkind == 0 ? p1 : p2, *pi = bestkind == 0 ? p2 : p1;
+  double nref[3]; /* outward normal of the reference face (points towards the incident box) */
+  for (int k = 0; k < 3; k++) nref[k] = bestkind == 0 ? bestn[k] : -bestn[k];
+  /* incident face: the face of the incident box most anti-parallel to nref */
+  int ia = 0; double mind = 1e30, isg = 1;
+  for (int a = 0; a < 3; a++) { double t = dot3(IB[a], nref); if (-fabs(t) < mind) { mind = -fabs(t); ia = a; isg = t > 0 ? -1 : 1; } }
+  int a1 = (ia + 1) % 3, a2 = (ia + 2) % 3;
+  double poly[16][3], tmp[16][3];
+  int np = 4;
+  for (int c = 0; c < 4; c++) {
+    double s1 = (c == 0 || c == 3) ? 1 : -1, s2 = (c < 2) ? 1 : -1;
+    for (int k = 0; k < 3; k++) poly[c][k] = pi[k] + isg * hi[ia] * IB[ia][k] + s1 * hi[a1] * IB[a1][k] + s2 * hi[a2] * IB[a2][k];
+  }
+  int r1 = (bi + 1) % 3, r2 = (bi + 2) % 3;
+  for (int side = 0; side < 4; side++) { /* clip against the four side planes of the reference face */
+    const double *ax = RA[side < 2 ? r1 : r2];
+    double sg = (side & 1) ? -1 : 1, lim = hr[side < 2 ? r1 : r2];
+    int nn = 0;
+    for (int c = 0; c < np; c++) {
+      const double *P = poly[c], *Q = poly[(c + 1) % np];
+      double rel1[3] = {P[0] - pr[0], P[1] - pr[1], P[2] - pr[2]}, rel2[3] = {Q[0] - pr[0], Q[1] - pr[1], Q[2] - pr[2]};
+      double dP = sg * dot3(rel1, ax) - lim, dQ = sg * dot3(rel2, ax) - lim;
+      if (dP <= 0) { memcpy(tmp[nn++], P, sizeof(double) * 3); }
+      if ((dP < 0 && dQ > 0) || (dP > 0 && dQ < 0)) {
+        double t = dP / (dP - dQ);
+        for (int k = 0; k < 3; k++) tmp[nn][k] = P[k] + t * (Q[k] - P[k]);
+        nn++;
+      }
+      if (nn >= 15) break;
+    }
+    np = nn;
+    memcpy(poly, tmp, sizeof(double) * 3 * np);
+    if (np == 0) return;
+  }
+  int cnt = 0;
+  for (int c = 0; c < np && cnt < 8; c++) {
+    double rel[3] = {poly[c][0] - pr[0], poly[c][1] - pr[1], poly[c][2] - pr[2]};
+    double depth = dot3(rel, nref) - hr[bi]; /* signed distance of the incident point from the reference face */
+    if (depth > margin) continue;
+    double pos[3];
+    for (int k = 0; k < 3; k++) pos[k] = poly[c][k] - nref[k] * depth * 0.5;
+    new_contact(d, m, pair, depth, pos, bestn);
+    cnt++;
+  }
+}
+
 static void make_frame(double *f) { /* mju_makeFrame with an undefined y axis */
   normalize3(f);
   f[3] = f[4] = f[5] = 0;
@@ -412,7 +523,8 @@ static void collision(const BrbRefModel *m, BrbRefData *d) {
     int t1 = m->geom_type[m->pair_geom1[p]], t2 = m->geom_type[m->pair_geom2[p]];
     if (t1 == BRB_GEOM_PLANE && t2 == BRB_GEOM_CYLINDER) collide_plane_cylinder(m, d, p);
     else if (t1 == BRB_GEOM_PLANE && t2 == BRB_GEOM_BOX) collide_plane_box(m, d, p);
-    /* box-box and cylinder-box (Env03 block) are not restated yet: SURVEY.md 8(f) row f2 */
+    else if (t1 == BRB_GEOM_BOX && t2 == BRB_GEOM_BOX) collide_box_box(m, d, p);
+    /* cylinder-box (wheel vs Env03 block; MuJoCo: libccd MPR) is not restated: such pairs produce no contacts here */
   }
   for (int i = 0; i < d->ncon; i++) make_frame(d->contact[i].frame);
 }

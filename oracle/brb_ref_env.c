@@ -15,6 +15,11 @@
  *   u_reset[12]     v2: obs pitch noise (RobotBaseEnv.py:224); v3: delay_target_speed draw (env01_v3.py:44)
  *   u_reset[13]     v2: pitch-dot noise (RobotBaseEnv.py:145);  v3: pitch_offset draw (env01_v3.py:52)
  * (v1 and v3 ignore the noise slots; v1/v2 ignore the v3 meaning of slots 12/13.)
+ *
+ * Env03-v2 (kind 3) uses wider rows: u_reset[32]: [0..15] np_random.uniform(-0.01, 0.01, 16) (env03_v1.py:61-63),
+ * [16..18] x/y/z_rot (env03_v1.py:67-70), [19..23] the five draws of set_block_pos_vel (env03_v2.py:42-53: target x,
+ * target z, block x/y/z_rot); u_step[8]: [0..4] the five draws of a re-fire inside step() (env03_v1.py:47-49), rest unused.
+ * attack_side_front (env03_v2.py:22, drawn once per env instance) is set with brb_ref_env_set_attack_side.
  */
 #include <math.h>
 #include <stdint.h>
@@ -32,11 +37,16 @@ static const double PITCH_MAX = 0.25, PITCH_DOT_MAX = 1, WHEEL_SPEED_MAX = 170.0
                     YAW_MAX = 45.0; /* RobotBaseEnv.py:19-23 */
 
 int brb_ref_sizeof_env(void) { return (int)sizeof(BrbRefEnv); }
+int brb_ref_reset_stride(int kind) { return kind == BRB_ENV03_V2 ? 32 : 16; }
+int brb_ref_step_stride(int kind) { return kind == BRB_ENV03_V2 ? 8 : 4; }
+void brb_ref_env_set_attack_side(BrbRefEnv *e, int front) { e->attack_side_front = front; }
 
 void brb_ref_env_init(BrbRefEnv *e, int kind, int max_episode_steps) {
   memset(e, 0, sizeof *e);
   e->kind = kind;
-  e->max_episode_steps = max_episode_steps; /* balance_robot/__init__.py:12-24 */
+  e->max_episode_steps = max_episode_steps; /* balance_robot/__init__.py:12-24, :47-52 */
+  e->block_delay = 0.5;                     /* env03_v2.py:23 */
+  e->attack_side_front = 1;
 }
 
 /* RobotBaseEnv.get_pitch (RobotBaseEnv.py:127-135): x angle of scipy as_euler('xyz') of the chassis
@@ -137,6 +147,23 @@ void brb_ref_euler_xyz_to_quat_xyzw(double a, double b, double c, double *out) {
   out[3] = ca * cb * cc + sa * sb * sc;
 }
 
+/* Env03_v2.set_block_pos_vel (env03_v2.py:25-59): fire the block at the robot from 0.3 m in front / behind.
+ * Reads the STALE robot xpos / xquat (Q1); u[0..4] = target x, target z, block x/y/z_rot. */
+static void set_block_pos_vel(BrbRefEnv *e, const double *u) {
+  const double *robot_pos = e->d.xpos[1];
+  double block_attack_angle = -brb_ref_env_yaw(e);
+  if (!e->attack_side_front) block_attack_angle += PI;
+  double block_pos[3] = {0.3 * sin(block_attack_angle) + robot_pos[0], 0.3 * cos(block_attack_angle) + robot_pos[1], 0.15};
+  double target[3] = {(u[0] - 0.5) * 0.02 + robot_pos[0], 0 + robot_pos[1], u[1] * 0.025 + 0.13};
+  double v[3] = {target[0] - block_pos[0], target[1] - block_pos[1], target[2] - block_pos[2]};
+  double nrm = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  for (int k = 0; k < 3; k++) v[k] = 7.5 * (v[k] / nrm);
+  double x_rot = u[2] * 2 * PI, y_rot = u[3] * 2 * PI, z_rot = u[4] * 2 * PI;
+  for (int k = 0; k < 3; k++) e->d.qpos[9 + k] = block_pos[k];
+  brb_ref_euler_xyz_to_quat_xyzw(x_rot, y_rot, z_rot, e->d.qpos + 12); /* same scalar-last-into-scalar-first quirk */
+  for (int k = 0; k < 3; k++) e->d.qvel[8 + k] = v[k];
+}
+
 /* MujocoEnv.reset -> mj_resetData -> reset_model (env01_v1.py:39-58, env01_v2.py:52-71, env01_v3.py:39-54) */
 void brb_ref_env_reset(const BrbRefModel *m, BrbRefEnv *e, const double *u_reset, float *obs) {
   brb_ref_reset_data(m, &e->d);
@@ -153,6 +180,19 @@ void brb_ref_env_reset(const BrbRefModel *m, BrbRefEnv *e, const double *u_reset
   for (int i = 0; i < m->nq; i++) qpos[i] = m->qpos0[i] + (-0.01 + (0.01 - -0.01) * u_reset[i]);
   qpos[2] = 0;
   double x_rot, y_rot, z_rot;
+  if (e->kind == BRB_ENV03_V2) { /* env03_v1.py:60-83 with Env03_v2.set_block_pos_vel */
+    x_rot = (u_reset[16] - 0.5) * 2 * PI;
+    y_rot = (u_reset[17] - 0.5) * 0.4;
+    z_rot = (u_reset[18] - 0.5) * 0.4;
+    brb_ref_euler_xyz_to_quat_xyzw(x_rot, y_rot, z_rot, qpos + 3);
+    memcpy(e->d.qpos, qpos, sizeof(double) * m->nq);
+    memset(e->d.qvel, 0, sizeof e->d.qvel);
+    brb_ref_forward(m, &e->d);
+    set_block_pos_vel(e, u_reset + 19);
+    e->has_block_timer = 0;
+    get_obs(e, 0, 0, obs);
+    return;
+  }
   x_rot = (u_reset[9] - 0.5) * 2 * PI;
   if (e->kind == BRB_ENV01_V2) {
     y_rot = (u_reset[10] - 0.5) * 0.2;
@@ -184,6 +224,18 @@ void brb_ref_env_step(const BrbRefModel *m, BrbRefEnv *e, const float *action, c
   e->d.ctrl[0] = e->d.qvel[6] + (double)action[0] * WHEEL_SPEED_DELTA_MAX;
   e->d.ctrl[1] = e->d.qvel[7] + (double)action[1] * WHEEL_SPEED_DELTA_MAX;
   brb_ref_step(m, &e->d, 250);
+  if (e->kind == BRB_ENV03_V2) { /* env03_v1.py:39-49 */
+    const double *bv = e->d.qvel + 8;
+    if (sqrt(bv[0] * bv[0] + bv[1] * bv[1] + bv[2] * bv[2]) < 0.1 && !e->has_block_timer) {
+      e->d.qpos[9] = 10; e->d.qpos[10] = 10; e->d.qpos[11] = 0; /* remove_block, env03_v1.py:85-86 */
+      e->has_block_timer = 1;
+      e->block_delay_time_start = e->d.time;
+    }
+    if (e->has_block_timer && (e->d.time - e->block_delay_time_start) > e->block_delay) {
+      set_block_pos_vel(e, u_step);
+      e->has_block_timer = 0;
+    }
+  }
   *terminated = fabs(get_pitch(e, u_step[1])) > (50 * PI / 180);
   get_obs(e, u_step[2], u_step[3], obs);
   e->elapsed_steps++;
@@ -238,7 +290,7 @@ static void *vec_worker(void *arg) {
   BrbRefVec *v = j->v;
   for (int i = j->lo; i < j->hi; i++) {
     if (j->is_reset) {
-      brb_ref_env_reset(&v->model, &v->envs[i], j->u_reset + 16 * (size_t)i, j->obs + 6 * (size_t)i);
+      brb_ref_env_reset(&v->model, &v->envs[i], j->u_reset + brb_ref_reset_stride(v->kind) * (size_t)i, j->obs + 6 * (size_t)i);
       v->ep_return[i] = 0;
       v->ep_len[i] = 0;
       continue;
@@ -246,7 +298,7 @@ static void *vec_worker(void *arg) {
     double r;
     int term, trunc;
     float o[6];
-    brb_ref_env_step(&v->model, &v->envs[i], j->actions + 2 * (size_t)i, j->u_step + 4 * (size_t)i, o, &r, &term, &trunc);
+    brb_ref_env_step(&v->model, &v->envs[i], j->actions + 2 * (size_t)i, j->u_step + brb_ref_step_stride(v->kind) * (size_t)i, o, &r, &term, &trunc);
     v->ep_return[i] += r;
     v->ep_len[i] += 1;
     j->reward[i] = (float)r;
@@ -256,7 +308,7 @@ static void *vec_worker(void *arg) {
     if (j->ep_len) j->ep_len[i] = v->ep_len[i];
     if (j->done[i]) {
       if (j->terminal_obs) memcpy(j->terminal_obs + 6 * (size_t)i, o, sizeof o);
-      brb_ref_env_reset(&v->model, &v->envs[i], j->u_reset + 16 * (size_t)i, o);
+      brb_ref_env_reset(&v->model, &v->envs[i], j->u_reset + brb_ref_reset_stride(v->kind) * (size_t)i, o);
       v->ep_return[i] = 0;
       v->ep_len[i] = 0;
     }
@@ -316,6 +368,18 @@ void brb_ref_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_
     k[1] += 0xBB67AE85u;
   }
   memcpy(out, c, sizeof c);
+}
+/* raw block access: out[n, 4*nblocks] = uniforms of blocks first_block .. first_block+nblocks-1 of `event` */
+void brb_ref_philox_blocks(uint64_t seed, uint64_t env0, int n, uint32_t event, uint32_t first_block, int nblocks, double *out) {
+  uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+  for (int i = 0; i < n; i++) {
+    uint64_t env = env0 + (uint64_t)i;
+    for (int b = 0; b < nblocks; b++) {
+      uint32_t ctr[4] = {(uint32_t)env, (uint32_t)(env >> 32), event, first_block + (uint32_t)b}, w[4];
+      brb_ref_philox4x32_10(ctr, key, w);
+      for (int k = 0; k < 4; k++) out[((size_t)i * nblocks + b) * 4 + k] = (double)(w[k] >> 8) * (1.0 / 16777216.0);
+    }
+  }
 }
 /* fills u_step[n,4] (block 0) and u_reset[n,16] (blocks 1..4) for event index `event` */
 void brb_ref_philox_draws(uint64_t seed, uint64_t env0, int n, uint32_t event, double *u_step, double *u_reset) {

@@ -16,7 +16,7 @@ LIB_PATH = HERE / "libbrb_ref.so"
 
 MAXBODY, MAXJNT, MAXNQ, MAXNV, MAXGEOM, MAXPAIR, MAXU, MAXCON, MAXEFC = 6, 6, 20, 16, 8, 16, 4, 32, 128
 FLAG_ACTDERIV_SKIP_CLAMPED, FLAG_RPY_FROM_FIRST_ROW = 1, 2
-ENV_KINDS = {"Env01-v1": 0, "Env01-v2": 1, "Env01-v3": 2}
+ENV_KINDS = {"Env01-v1": 0, "Env01-v2": 1, "Env01-v3": 2, "Env03-v2": 3}
 
 d, i = C.c_double, C.c_int
 
@@ -73,6 +73,7 @@ class RefEnv(C.Structure):
         ("kind", i), ("max_episode_steps", i), ("elapsed_steps", i), ("has_last", i),
         ("last_time", d), ("last_pitch", d), ("target_wheel_speed", d), ("target_yaw", d),
         ("delay_target_speed", d), ("pitch_offset", d),
+        ("has_block_timer", i), ("attack_side_front", i), ("block_delay_time_start", d), ("block_delay", d),
         ("d", RefData),
     ]
 
@@ -175,12 +176,33 @@ def philox_draws(seed: int, env0: int, n: int, event: int):
     return us, ur
 
 
+def philox_blocks(seed: int, env0: int, n: int, event: int, first_block: int, nblocks: int) -> np.ndarray:
+    out = np.empty((n, 4 * nblocks), np.float64)
+    lib().brb_ref_philox_blocks(C.c_uint64(seed), C.c_uint64(env0), n, C.c_uint32(event), C.c_uint32(first_block), nblocks,
+                                C.c_void_p(out.ctypes.data))
+    return out
+
+
+ATTACK_SIDE_EVENT = 0xFFFFFFFF
+
+
+def env03_draws(seed: int, env0: int, n: int, event: int):
+    """(u_step[n,8], u_reset[n,32]) for Env03-v2: reset rows = Philox blocks 1..8, re-fire rows = blocks 9..10."""
+    return philox_blocks(seed, env0, n, event, 9, 2), philox_blocks(seed, env0, n, event, 1, 8)
+
+
+def env03_attack_side(seed: int, env0: int, n: int) -> np.ndarray:
+    """attack_side_front = np.random.random() > 0.5, drawn once per env instance (env03_v2.py:22)."""
+    return philox_blocks(seed, env0, n, ATTACK_SIDE_EVENT, 0, 1)[:, 0] > 0.5
+
+
 class RefVecEnv:
     """Vectorised oracle env (DummyVecEnv + TimeLimit + Monitor semantics), draws injected per call."""
 
     def __init__(self, spec, env_id: str, n: int, max_episode_steps: int, nthreads: int = 1, flags=None):
         self.model = model_from_spec(spec) if flags is None else model_from_spec(spec, flags)
         self.n, self.nthreads, self.kind = n, nthreads, ENV_KINDS[env_id]
+        self.reset_stride, self.step_stride = (32, 8) if self.kind == 3 else (16, 4)
         self._h = C.c_void_p()
         rc = lib().brb_ref_vec_create(C.byref(self.model), self.kind, max_episode_steps, n, C.byref(self._h))
         if rc != 0:
@@ -193,12 +215,16 @@ class RefVecEnv:
         self.ep_return = np.zeros(n, np.float32)
         self.ep_len = np.zeros(n, np.int32)
 
+    def set_attack_side(self, front) -> None:
+        for k in range(self.n):
+            lib().brb_ref_env_set_attack_side(C.byref(self.env(k)), int(bool(front[k])))
+
     def env(self, k: int) -> RefEnv:
         return lib().brb_ref_vec_env(self._h, k).contents
 
     def reset(self, u_reset: np.ndarray) -> np.ndarray:
         u_reset = np.ascontiguousarray(u_reset, np.float64)
-        assert u_reset.shape == (self.n, 16)
+        assert u_reset.shape == (self.n, self.reset_stride)
         lib().brb_ref_vec_reset(self._h, u_reset.ctypes.data, self.obs.ctypes.data, self.nthreads)
         return self.obs.copy()
 
@@ -206,7 +232,7 @@ class RefVecEnv:
         actions = np.ascontiguousarray(actions, np.float32)
         u_step = np.ascontiguousarray(u_step, np.float64)
         u_reset = np.ascontiguousarray(u_reset, np.float64)
-        assert actions.shape == (self.n, 2) and u_step.shape == (self.n, 4) and u_reset.shape == (self.n, 16)
+        assert actions.shape == (self.n, 2) and u_step.shape == (self.n, self.step_stride) and u_reset.shape == (self.n, self.reset_stride)
         lib().brb_ref_vec_step(self._h, actions.ctypes.data, u_step.ctypes.data, u_reset.ctypes.data,
                                self.obs.ctypes.data, self.reward.ctypes.data, self.done.ctypes.data,
                                self.truncated.ctypes.data, self.terminal_obs.ctypes.data,
