@@ -78,8 +78,9 @@ class PyRefEnv03(PyRefEnv):
         self.draws = list(draws)
         self._sync()
         reward = self._get_reward()
-        self.d.ctrl[0] = self.d.qvel[6] + a[0] * 4.0
-        self.d.ctrl[1] = self.d.qvel[7] + a[1] * 4.0
+        # data.joint(...).qvel[0] is a numpy float64 scalar in the reference (float64 + float32 -> float64)
+        self.d.ctrl[0] = np.float64(self.d.qvel[6]) + a[0] * 4.0
+        self.d.ctrl[1] = np.float64(self.d.qvel[7]) + a[1] * 4.0
         self.L.brb_ref_step(C.byref(self.m), C.byref(self.d), 250)
         block_vel_vec = np.array(ref.arr(self.d.qvel, 14)[8:11])
         if np.linalg.norm(block_vel_vec) < 0.1 and self.block_delay_time_start is None:
