@@ -62,7 +62,8 @@ extern "C" const char *brb_strerror(int code) {
 
 extern "C" int brb_model_create(const BrbModelConsts *consts, const double *time_table_host, int n_time, int device, BrbModel **out) {
   if (!consts || !time_table_host || !out || n_time < consts->max_episode_steps + 2) return BRB_EINVAL;
-  if (consts->env_kind < BRB_ENV01_V1 || consts->env_kind > BRB_ENV01_V3 || consts->frame_skip < 1) return BRB_EINVAL;
+  if (consts->env_kind < BRB_ENV01_V1 || consts->env_kind > BRB_ENV03_V2 || consts->frame_skip < 1) return BRB_EINVAL;
+  if (consts->nq < 9 || consts->nq > 16 || consts->nv < 8 || consts->nv > 14) return BRB_EINVAL;
   CK(cudaSetDevice(device));
   BrbModel *m = (BrbModel *)calloc(1, sizeof(BrbModel));
   if (!m) return BRB_ENOMEM;
@@ -92,8 +93,9 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
   if (!e) return BRB_ENOMEM;
   e->model = m;
   const size_t N = (size_t)n;
+  const size_t NQ = (size_t)m->consts.nq, NV = (size_t)m->consts.nv;
   const size_t sz[] = {
-      align_up(9 * N * 8), align_up(8 * N * 8), align_up(4 * N * 8), align_up(8 * N * 4), align_up(N * 8), align_up(N * 8),
+      align_up(NQ * N * 8), align_up(NV * N * 8), align_up(4 * N * 8), align_up(8 * N * 4), align_up(N * 8), align_up(N * 8),
       align_up(3 * N * 8), align_up(N * 4), align_up(N * 4), align_up(N * 4), align_up(BRB_NSTATS * 8), align_up(N * 4), align_up(N), align_up(4 * 32 * 4),
       // staging
       align_up(2 * N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(N), align_up(N), align_up(N * 4)};
@@ -128,6 +130,8 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
   e->d_eplen = TAKE(int32_t);
 #undef TAKE
   e->S.n = n;
+  e->S.nq = m->consts.nq;
+  e->S.nv = m->consts.nv;
   e->S.env0 = env_id_offset;
   e->S.seed = seed;
   e->S.time_table = m->time_table;

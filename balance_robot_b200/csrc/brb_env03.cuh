@@ -1,0 +1,763 @@
+// brb_env03.cuh — Env03-v2: the balance robot plus a free 4 cm block fired at it (reference envs/env03_v1.py:17-113,
+// envs/env03_v2.py:14-59, scene envs/env03_v1.xml:31-37).  Included by brb_kernels.cu (same translation unit, so it
+// shares the robot physics, Philox and task-logic helpers).
+//
+// What changes against Env01: there are no explicit contact pairs, so every pair is a *dynamic* pair
+// with mixed default parameters — mu = 1, position-dependent impedance (solimp 0.9/0.95/0.001), the block geom's margin
+// 0.002 and solref (0.005, 0.9) averaged in.  Contacts modelled: wheel-floor (plane-cylinder), block-floor (plane-box),
+// chassis-block (box-box: SAT + face clipping, the oracle's algorithm in fp32).  Not modelled (counted as unsupported):
+// wheel-block (MuJoCo uses libccd MPR there) and chassis-floor.
+//
+// Solver structure per substep: while the block does not touch the chassis the two systems are independent — the
+// robot's 8x8 (same code as Env01 with per-contact row weights) and the block's 6x6 (isotropic cube, M = diag(m, I)).
+// During an impact (a few ms every 0.5 s+) all contacts go through one generic dense 14-dof Newton solve
+// (env03_coupled_solve, local-memory arrays, not inlined: rare path).
+#ifndef BRB_ENV03_CUH
+#define BRB_ENV03_CUH
+
+#define LT6(i, j) ((i) * ((i) + 1) / 2 + (j))
+
+struct Blk {
+  // state (plain fp32: the block only has to agree with the oracle to the 1e-5 bar, and it does without compensation)
+  float p[3], q[4], v[3], w[3];   // world position, quaternion (w,x,y,z), world linear velocity, BODY angular velocity
+  // working set of the current substep
+  float ex[3], ey[3], ez[3];      // columns of the block's rotation matrix
+  float cr[4][3], cy[4][3], cD[4];   // floor contacts: point relative to the block centre, yhat, row weight (dynamic index: local memory)
+  int nc;                         // number of floor contacts (<= 4)
+  unsigned bits;                  // active pyramid rows, 4 bits per contact slot
+};
+
+BRB_D void blk_frame(Blk &B) {
+  const float qw = B.q[0], qx = B.q[1], qy = B.q[2], qz = B.q[3];
+  const float xx = qx * qx, yy = qy * qy, zz = qz * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz, wx = qw * qx, wy = qw * qy, wz = qw * qz;
+  B.ex[0] = 1.f - 2.f * (yy + zz); B.ey[0] = 2.f * (xy - wz); B.ez[0] = 2.f * (xz + wy);
+  B.ex[1] = 2.f * (xy + wz); B.ey[1] = 1.f - 2.f * (xx + zz); B.ez[1] = 2.f * (yz - wx);
+  B.ex[2] = 2.f * (xz - wy); B.ey[2] = 2.f * (yz + wx); B.ez[2] = 1.f - 2.f * (xx + yy);
+}
+
+// plane-box (mjc_PlaneBox, A.6): corners in index order, at most 4, skipping corners above the centre
+BRB_D void blk_setup(const BrbModelConsts &c, Blk &B) {
+  blk_frame(B);
+  B.nc = 0;
+  const float h = c.blk_half, *pp = c.pp[1];
+  const float dist0 = (B.p[2] - c.zfloor) - c.zfloor_lo;
+  if (dist0 - c.blk_radius > pp[7]) return;
+  const float wwx = B.ex[0] * B.w[0] + B.ey[0] * B.w[1] + B.ez[0] * B.w[2];   // world angular velocity
+  const float wwy = B.ex[1] * B.w[0] + B.ey[1] * B.w[1] + B.ez[1] * B.w[2];
+  const float wwz = B.ex[2] * B.w[0] + B.ey[2] * B.w[1] + B.ez[2] * B.w[2];
+  for (int i = 0; i < 8 && B.nc < 4; i++) {
+    const float sx = (i & 1) ? h : -h, sy = (i & 2) ? h : -h, sz = (i & 4) ? h : -h;
+    const float cx = B.ex[0] * sx + B.ey[0] * sy + B.ez[0] * sz;
+    const float cy = B.ex[1] * sx + B.ey[1] * sy + B.ez[1] * sz;
+    const float cz = B.ex[2] * sx + B.ey[2] * sy + B.ez[2] * sz;
+    const float dist = dist0 + cz;
+    if (dist > pp[7] || cz > 0.f) continue;
+    if (dist >= pp[7]) { continue; }            // inside the margin band edge: no constraint row (dist >= includemargin)
+    const int k = B.nc++;
+    const float rz = cz - 0.5f * dist;
+    const float px = B.v[0] + wwy * rz - wwz * cy, py = B.v[1] + wwz * cx - wwx * rz, pz = B.v[2] + wwx * cy - wwy * cx;
+    const float imp = imp_of(pp, dist);
+    B.cr[k][0] = cx; B.cr[k][1] = cy; B.cr[k][2] = rz;
+    B.cD[k] = pp[3] * imp / (1.f - imp);
+    B.cy[k][0] = pp[2] * pz + pp[1] * imp * (dist - pp[7]);
+    B.cy[k][1] = pp[2] * py;
+    B.cy[k][2] = -pp[2] * px;
+  }
+}
+
+BRB_D unsigned blk_active_set(const BrbModelConsts &c, const Blk &B, const float (&a)[6], unsigned prev) {
+  unsigned bits = 0;
+  const float mu = c.pp[1][0], eps = 2e-4f;
+  for (int k = 0; k < B.nc; k++) {
+    const float rx = B.cr[k][0], ry = B.cr[k][1], rz = B.cr[k][2];
+    const float px = a[0] + a[4] * rz - a[5] * ry, py = a[1] + a[5] * rx - a[3] * rz, pz = a[2] + a[3] * ry - a[4] * rx;
+    const float z0 = pz + B.cy[k][0], z1 = mu * (py + B.cy[k][1]), z2 = mu * (B.cy[k][2] - px);
+    const unsigned pb = prev >> (4 * k);
+    const float e0 = (pb & 1u) ? eps : -eps, e1 = (pb & 2u) ? eps : -eps, e2 = (pb & 4u) ? eps : -eps, e3 = (pb & 8u) ? eps : -eps;
+    bits |= ((unsigned)(z0 + z1 < e0) | ((unsigned)(z0 - z1 < e1) << 1) | ((unsigned)(z0 + z2 < e2) << 2) | ((unsigned)(z0 - z2 < e3) << 3)) << (4 * k);
+  }
+  return bits;
+}
+
+// block alone: (diag(m, I) + sum P' S P) a = f - sum P' S yhat, P = [1 | -[r]x], world coordinates
+BRB_D void blk_solve(const BrbModelConsts &c, const Blk &B, unsigned bits, float (&a)[6]) {
+  float H[21], r[6];
+#pragma unroll
+  for (int k = 0; k < 21; k++) H[k] = 0.f;
+  H[LT6(0, 0)] = c.blk_mass; H[LT6(1, 1)] = c.blk_mass; H[LT6(2, 2)] = c.blk_mass;
+  H[LT6(3, 3)] = c.blk_inertia; H[LT6(4, 4)] = c.blk_inertia; H[LT6(5, 5)] = c.blk_inertia;
+  r[0] = 0.f; r[1] = 0.f; r[2] = -c.blk_mass * c.grav; r[3] = 0.f; r[4] = 0.f; r[5] = 0.f;
+  const float mu = c.pp[1][0];
+  for (int k = 0; k < B.nc; k++) {
+    const unsigned b = (bits >> (4 * k)) & 15u;
+    if (!b) continue;
+    const float b0 = (float)(b & 1u), b1 = (float)((b >> 1) & 1u), b2 = (float)((b >> 2) & 1u), b3 = (float)((b >> 3) & 1u);
+    const float Dc = B.cD[k], Dm = Dc * mu, Dmm = Dm * mu;
+    const float Szz = Dc * (b0 + b1 + b2 + b3), Syz = Dm * (b0 - b1), Sxz = -Dm * (b2 - b3), Syy = Dmm * (b0 + b1), Sxx = Dmm * (b2 + b3);
+    const float rx = B.cr[k][0], ry = B.cr[k][1], rz = B.cr[k][2];
+    const float T3x = Sxz * ry, T3y = -Syy * rz + Syz * ry, T3z = -Syz * rz + Szz * ry;
+    const float T4x = Sxx * rz - Sxz * rx, T4y = -Syz * rx, T4z = Sxz * rz - Szz * rx;
+    const float T5x = -Sxx * ry, T5y = Syy * rx, T5z = -Sxz * ry + Syz * rx;
+    H[LT6(0, 0)] += Sxx; H[LT6(2, 0)] += Sxz; H[LT6(1, 1)] += Syy; H[LT6(2, 1)] += Syz; H[LT6(2, 2)] += Szz;
+    H[LT6(3, 0)] += T3x; H[LT6(3, 1)] += T3y; H[LT6(3, 2)] += T3z;
+    H[LT6(4, 0)] += T4x; H[LT6(4, 1)] += T4y; H[LT6(4, 2)] += T4z;
+    H[LT6(5, 0)] += T5x; H[LT6(5, 1)] += T5y; H[LT6(5, 2)] += T5z;
+    H[LT6(3, 3)] += -rz * T3y + ry * T3z;
+    H[LT6(4, 3)] += rz * T3x - rx * T3z;
+    H[LT6(5, 3)] += -ry * T3x + rx * T3y;
+    H[LT6(4, 4)] += rz * T4x - rx * T4z;
+    H[LT6(5, 4)] += -ry * T4x + rx * T4y;
+    H[LT6(5, 5)] += -ry * T5x + rx * T5y;
+    const float y0 = B.cy[k][0], y1 = B.cy[k][1], y2 = B.cy[k][2];
+    const float gx = Sxx * y2 - Sxz * y0, gy = -(Syy * y1 + Syz * y0), gz = Sxz * y2 - Syz * y1 - Szz * y0;
+    r[0] += gx; r[1] += gy; r[2] += gz;
+    r[3] += -rz * gy + ry * gz;
+    r[4] += rz * gx - rx * gz;
+    r[5] += -ry * gx + rx * gy;
+  }
+#include "brb_chol6.inc"
+#pragma unroll
+  for (int k = 0; k < 6; k++) a[k] = r[k];
+}
+
+// semi-implicit Euler for the free cube (no joint damping, no actuator: implicitfast reduces to Euler)
+BRB_D void blk_finalize(const BrbModelConsts &c, Blk &B, const float (&a)[6]) {
+  const float h = c.h;
+  B.v[0] += h * a[0]; B.v[1] += h * a[1]; B.v[2] += h * a[2];
+  B.w[0] += h * (B.ex[0] * a[3] + B.ex[1] * a[4] + B.ex[2] * a[5]);      // body-frame angular acceleration = R' alpha_w
+  B.w[1] += h * (B.ey[0] * a[3] + B.ey[1] * a[4] + B.ey[2] * a[5]);
+  B.w[2] += h * (B.ez[0] * a[3] + B.ez[1] * a[4] + B.ez[2] * a[5]);
+  B.p[0] += h * B.v[0]; B.p[1] += h * B.v[1]; B.p[2] += h * B.v[2];
+  const float qw = B.q[0], qx = B.q[1], qy = B.q[2], qz = B.q[3];
+  const float t2 = (h * h) * (B.w[0] * B.w[0] + B.w[1] * B.w[1] + B.w[2] * B.w[2]);
+  const float sn = (0.5f * h) * (1.f - t2 * (1.f / 24.f)), cm1 = -(0.125f * t2) * (1.f - t2 * (1.f / 48.f));
+  const float ex = sn * B.w[0], ey = sn * B.w[1], ez = sn * B.w[2];
+  float nw = qw + (qw * cm1 - (qx * ex + qy * ey + qz * ez));
+  float nx = qx + (qx * cm1 + (qw * ex + qy * ez - qz * ey));
+  float ny = qy + (qy * cm1 + (qw * ey - qx * ez + qz * ex));
+  float nz = qz + (qz * cm1 + (qw * ez + qx * ey - qy * ex));
+  const float inv = rsqrtf(nw * nw + nx * nx + ny * ny + nz * nz);
+  B.q[0] = nw * inv; B.q[1] = nx * inv; B.q[2] = ny * inv; B.q[3] = nz * inv;
+}
+
+// ------------------------------------------------------------------------------------------------ chassis-block (box-box)
+// Generic contact record of the coupled path.  Bodies: A (normal points away from it) and B; either may be the robot
+// (ra, wheel column) or the block (rb) or the world (absent).
+struct GContact {
+  float n[3], t1[3], t2[3];     // contact frame (world)
+  float ra[3], wa[3];           // robot: point relative to the chassis origin, wheel column (zero for chassis contacts)
+  float rb[3];                  // block: point relative to its centre
+  float y[3], D, mu;
+  int robot_sign, block_sign, wheel;   // +1 body B, -1 body A, 0 absent; wheel = 0/1 or -1
+};
+#define BRB_MAXGC 16
+
+BRB_D void make_frame3(float *n, float *t1, float *t2) {   // mju_makeFrame with an undefined y axis (A.6)
+  t1[0] = 0.f; t1[1] = 0.f; t1[2] = 0.f;
+  if (n[1] < 0.5f && n[1] > -0.5f) t1[1] = 1.f; else t1[2] = 1.f;
+  const float d = n[0] * t1[0] + n[1] * t1[1] + n[2] * t1[2];
+  t1[0] -= d * n[0]; t1[1] -= d * n[1]; t1[2] -= d * n[2];
+  const float inv = rsqrtf(t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2]);
+  t1[0] *= inv; t1[1] *= inv; t1[2] *= inv;
+  t2[0] = n[1] * t1[2] - n[2] * t1[1]; t2[1] = n[2] * t1[0] - n[0] * t1[2]; t2[2] = n[0] * t1[1] - n[1] * t1[0];
+}
+
+BRB_D float dot3f(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+
+// SAT over 15 axes + face clipping / edge-edge closest points: the oracle's collide_box_box in fp32.  Box 1 = chassis
+// (centre p1, axes A[i], half sizes h1), box 2 = block.  Returns the number of contacts; pos/dist/normal (1 -> 2) out.
+#ifdef BRB_HOST_EMU
+static
+#else
+__device__ __noinline__
+#endif
+int env03_box_box(const float *p1, const float (*A)[3], const float *h1, const float *p2, const float (*Bx)[3], const float *h2,
+                  float margin, float (*pos)[3], float *dist, float *nrm) {
+  const float dp[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
+  float best = -1e30f, bestn[3] = {0.f, 0.f, 1.f};
+  int bestkind = -1, bi = 0, bj = 0;
+  for (int kind = 0; kind < 2; kind++)
+    for (int i = 0; i < 3; i++) {
+      const float *L = kind == 0 ? A[i] : Bx[i];
+      float r1 = 0.f, r2 = 0.f;
+      for (int k = 0; k < 3; k++) { r1 += h1[k] * fabsf(dot3f(A[k], L)); r2 += h2[k] * fabsf(dot3f(Bx[k], L)); }
+      const float t = dot3f(dp, L), s = fabsf(t) - (r1 + r2);
+      if (s > margin) return 0;
+      if (s > best) { best = s; bestkind = kind; bi = i; for (int k = 0; k < 3; k++) bestn[k] = t >= 0.f ? L[k] : -L[k]; }
+    }
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      float L[3] = {A[i][1] * Bx[j][2] - A[i][2] * Bx[j][1], A[i][2] * Bx[j][0] - A[i][0] * Bx[j][2], A[i][0] * Bx[j][1] - A[i][1] * Bx[j][0]};
+      const float n = sqrtf(dot3f(L, L));
+      if (n < 1e-6f) continue;
+      for (int k = 0; k < 3; k++) L[k] /= n;
+      float r1 = 0.f, r2 = 0.f;
+      for (int k = 0; k < 3; k++) { r1 += h1[k] * fabsf(dot3f(A[k], L)); r2 += h2[k] * fabsf(dot3f(Bx[k], L)); }
+      const float t = dot3f(dp, L), s = fabsf(t) - (r1 + r2);
+      if (s > margin) return 0;
+      if (s > best + 1e-4f) { best = s; bestkind = 2; bi = i; bj = j; for (int k = 0; k < 3; k++) bestn[k] = t >= 0.f ? L[k] : -L[k]; }
+    }
+  for (int k = 0; k < 3; k++) nrm[k] = bestn[k];
+  if (bestkind == 2) {
+    float c1[3] = {p1[0], p1[1], p1[2]}, c2[3] = {p2[0], p2[1], p2[2]};
+    for (int a = 0; a < 3; a++) {
+      if (a != bi) { const float sg = dot3f(A[a], bestn) > 0.f ? 1.f : -1.f; for (int k = 0; k < 3; k++) c1[k] += sg * h1[a] * A[a][k]; }
+      if (a != bj) { const float sg = dot3f(Bx[a], bestn) > 0.f ? -1.f : 1.f; for (int k = 0; k < 3; k++) c2[k] += sg * h2[a] * Bx[a][k]; }
+    }
+    const float *u = A[bi], *v = Bx[bj];
+    const float w[3] = {c1[0] - c2[0], c1[1] - c2[1], c1[2] - c2[2]};
+    const float uv = dot3f(u, v), uw = dot3f(u, w), vw = dot3f(v, w), den = 1.f - uv * uv;
+    float sa = den > 1e-12f ? (uv * vw - uw) / den : 0.f, sb = den > 1e-12f ? (vw - uv * uw) / den : 0.f;
+    sa = fmaxf(-h1[bi], fminf(h1[bi], sa)); sb = fmaxf(-h2[bj], fminf(h2[bj], sb));
+    for (int k = 0; k < 3; k++) pos[0][k] = 0.5f * ((c1[k] + sa * u[k]) + (c2[k] + sb * v[k]));
+    dist[0] = best;
+    return 1;
+  }
+  const float (*RA)[3] = bestkind == 0 ? A : Bx, (*IB)[3] = bestkind == 0 ? Bx : A;
+  const float *hr = bestkind == 0 ? h1 : h2, *hi = bestkind == 0 ? h2 : h1, *pr = bestkind == 0 ? p1 : p2, *pi = bestkind == 0 ? p2 : p1;
+  float nref[3];
+  for (int k = 0; k < 3; k++) nref[k] = bestkind == 0 ? bestn[k] : -bestn[k];
+  int ia = 0; float mind = 1e30f, isg = 1.f;
+  for (int a = 0; a < 3; a++) { const float t = dot3f(IB[a], nref); if (-fabsf(t) < mind) { mind = -fabsf(t); ia = a; isg = t > 0.f ? -1.f : 1.f; } }
+  const int a1 = (ia + 1) % 3, a2 = (ia + 2) % 3;
+  float poly[16][3], tmp[16][3];
+  int np = 4;
+  for (int cc = 0; cc < 4; cc++) {
+    const float s1 = (cc == 0 || cc == 3) ? 1.f : -1.f, s2 = (cc < 2) ? 1.f : -1.f;
+    for (int k = 0; k < 3; k++) poly[cc][k] = pi[k] + isg * hi[ia] * IB[ia][k] + s1 * hi[a1] * IB[a1][k] + s2 * hi[a2] * IB[a2][k];
+  }
+  const int r1 = (bi + 1) % 3, r2 = (bi + 2) % 3;
+  for (int side = 0; side < 4; side++) {
+    const float *ax = RA[side < 2 ? r1 : r2];
+    const float sg = (side & 1) ? -1.f : 1.f, lim = hr[side < 2 ? r1 : r2];
+    int nn = 0;
+    for (int cc = 0; cc < np; cc++) {
+      const float *P = poly[cc], *Q = poly[(cc + 1) % np];
+      const float e1[3] = {P[0] - pr[0], P[1] - pr[1], P[2] - pr[2]}, e2[3] = {Q[0] - pr[0], Q[1] - pr[1], Q[2] - pr[2]};
+      const float dP = sg * dot3f(e1, ax) - lim, dQ = sg * dot3f(e2, ax) - lim;
+      if (dP <= 0.f) { for (int k = 0; k < 3; k++) tmp[nn][k] = P[k]; nn++; }
+      if ((dP < 0.f && dQ > 0.f) || (dP > 0.f && dQ < 0.f)) {
+        const float t = dP / (dP - dQ);
+        for (int k = 0; k < 3; k++) tmp[nn][k] = P[k] + t * (Q[k] - P[k]);
+        nn++;
+      }
+      if (nn >= 15) break;
+    }
+    np = nn;
+    for (int cc = 0; cc < np; cc++) for (int k = 0; k < 3; k++) poly[cc][k] = tmp[cc][k];
+    if (np == 0) return 0;
+  }
+  int cnt = 0;
+  for (int cc = 0; cc < np && cnt < 8; cc++) {
+    const float rel[3] = {poly[cc][0] - pr[0], poly[cc][1] - pr[1], poly[cc][2] - pr[2]};
+    const float depth = dot3f(rel, nref) - hr[bi];
+    if (depth > margin) continue;
+    for (int k = 0; k < 3; k++) pos[cnt][k] = poly[cc][k] - nref[k] * depth * 0.5f;
+    dist[cnt] = depth;
+    cnt++;
+  }
+  return cnt;
+}
+
+// Generic dense Newton solve over all 14 dofs (robot: world lin, world ang, wheels; block: world lin, world ang) for the
+// substeps in which the block touches the chassis.  Active-set iteration with hysteresis, exact for a fixed set.
+#ifdef BRB_HOST_EMU
+static
+#else
+__device__ __noinline__
+#endif
+int env03_coupled_solve(const BrbModelConsts &c, const Phys &P, const GContact *gc, int ngc, float *acc /*[14]*/) {
+  float J[BRB_MAXGC * 3][14];
+  for (int k = 0; k < ngc; k++) {
+    const GContact &g = gc[k];
+    const float *dirs[3] = {g.n, g.t1, g.t2};
+    for (int r = 0; r < 3; r++) {
+      const float *d = dirs[r];
+      float *row = J[3 * k + r];
+      for (int j = 0; j < 14; j++) row[j] = 0.f;
+      if (g.robot_sign) {
+        const float s = (float)g.robot_sign;
+        row[0] = s * d[0]; row[1] = s * d[1]; row[2] = s * d[2];
+        row[3] = s * (g.ra[1] * d[2] - g.ra[2] * d[1]); row[4] = s * (g.ra[2] * d[0] - g.ra[0] * d[2]); row[5] = s * (g.ra[0] * d[1] - g.ra[1] * d[0]);
+        if (g.wheel >= 0) row[6 + g.wheel] = s * dot3f(g.wa, d);
+      }
+      if (g.block_sign) {
+        const float s = (float)g.block_sign;
+        row[8] = s * d[0]; row[9] = s * d[1]; row[10] = s * d[2];
+        row[11] = s * (g.rb[1] * d[2] - g.rb[2] * d[1]); row[12] = s * (g.rb[2] * d[0] - g.rb[0] * d[2]); row[13] = s * (g.rb[0] * d[1] - g.rb[1] * d[0]);
+      }
+    }
+  }
+  // mass matrix in these coordinates (robot block as in phys_solve, block diagonal) and smooth force
+  float M[14][14], f[14];
+  for (int i = 0; i < 14; i++) for (int j = 0; j < 14; j++) M[i][j] = 0.f;
+  {
+    M[0][0] = M[1][1] = M[2][2] = c.mass;
+    const float kx = c.mcz * P.ez[0], ky = c.mcz * P.ez[1], kz = c.mcz * P.ez[2];
+    M[4][0] = kz; M[5][0] = -ky; M[3][1] = -kz; M[5][1] = kx; M[3][2] = ky; M[4][2] = -kx;
+    const float dx = c.Ixx - c.Iyy, dz = c.Izz - c.Iyy;
+    for (int i = 0; i < 3; i++) for (int j = 0; j <= i; j++) M[3 + i][3 + j] = (i == j ? c.Iyy : 0.f) + dx * P.ex[i] * P.ex[j] + dz * P.ez[i] * P.ez[j];
+    for (int j = 0; j < 3; j++) { M[6][3 + j] = -c.Ia * P.ex[j]; M[7][3 + j] = c.Ia * P.ex[j]; }
+    M[6][6] = M[7][7] = c.Ia;
+    M[8][8] = M[9][9] = M[10][10] = c.blk_mass;
+    M[11][11] = M[12][12] = M[13][13] = c.blk_inertia;
+    for (int i = 0; i < 14; i++) for (int j = i + 1; j < 14; j++) M[i][j] = M[j][i];
+    for (int k = 0; k < 8; k++) f[k] = P.f[k];
+    f[8] = 0.f; f[9] = 0.f; f[10] = -c.blk_mass * c.grav; f[11] = f[12] = f[13] = 0.f;
+  }
+  // Newton with an exact line search on the piecewise-quadratic cost (the oracle's algorithm, A.8): start from the
+  // unconstrained acceleration, direction p = -H^-1 g on the current active set, full step if it keeps the set (then the
+  // point is the exact minimiser), otherwise the root of the increasing piecewise-linear phi'(alpha).
+  const int nrow = 4 * ngc;
+  float a[14], jar[4 * BRB_MAXGC], jp[4 * BRB_MAXGC], Dr[4 * BRB_MAXGC];
+  int nonconv = 0;
+  {
+    float L[14][14], r[14];
+    for (int i = 0; i < 14; i++) { r[i] = f[i]; for (int j = 0; j <= i; j++) L[i][j] = M[i][j]; }
+    for (int j = 0; j < 14; j++) {
+      float d = L[j][j];
+      for (int k = 0; k < j; k++) d -= L[j][k] * L[j][k];
+      const float id = rsqrtf(d);
+      L[j][j] = id;
+      for (int i = j + 1; i < 14; i++) { float t = L[i][j]; for (int k = 0; k < j; k++) t -= L[i][k] * L[j][k]; L[i][j] = t * id; }
+    }
+    for (int i = 0; i < 14; i++) { float t = r[i]; for (int k = 0; k < i; k++) t -= L[i][k] * r[k]; r[i] = t * L[i][i]; }
+    for (int i = 13; i >= 0; i--) { float t = r[i]; for (int k = i + 1; k < 14; k++) t -= L[k][i] * r[k]; r[i] = t * L[i][i]; }
+    for (int i = 0; i < 14; i++) a[i] = r[i];
+  }
+  for (int it = 0;; it++) {
+    float H[14][14], g[14], p[14];
+    for (int i = 0; i < 14; i++) {
+      float t = -f[i];
+      for (int j = 0; j < 14; j++) t += M[i][j] * a[j];
+      g[i] = t;
+      for (int j = 0; j <= i; j++) H[i][j] = M[i][j];
+    }
+    for (int k = 0; k < ngc; k++) {
+      const GContact &gk = gc[k];
+      for (int rr = 0; rr < 4; rr++) {
+        const float *jt = J[3 * k + 1 + (rr >> 1)], sg = (rr & 1) ? -gk.mu : gk.mu;
+        float row[14], z = gk.y[0] + sg * gk.y[1 + (rr >> 1)];
+        for (int j = 0; j < 14; j++) { row[j] = J[3 * k][j] + sg * jt[j]; z += row[j] * a[j]; }
+        jar[4 * k + rr] = z;
+        Dr[4 * k + rr] = gk.D;
+        if (z < 0.f) {
+          for (int i = 0; i < 14; i++) {
+            const float di = gk.D * row[i];
+            if (di == 0.f) continue;
+            g[i] += di * z;
+            for (int j = 0; j <= i; j++) H[i][j] += di * row[j];
+          }
+        }
+      }
+    }
+    for (int j = 0; j < 14; j++) {   // Cholesky (lower), in place; diagonal keeps 1/L_jj
+      float d = H[j][j];
+      for (int k = 0; k < j; k++) d -= H[j][k] * H[j][k];
+      const float id = rsqrtf(d);
+      H[j][j] = id;
+      for (int i = j + 1; i < 14; i++) { float t = H[i][j]; for (int k = 0; k < j; k++) t -= H[i][k] * H[j][k]; H[i][j] = t * id; }
+    }
+    for (int i = 0; i < 14; i++) { float t = -g[i]; for (int k = 0; k < i; k++) t -= H[i][k] * p[k]; p[i] = t * H[i][i]; }
+    for (int i = 13; i >= 0; i--) { float t = p[i]; for (int k = i + 1; k < 14; k++) t -= H[k][i] * p[k]; p[i] = t * H[i][i]; }
+    bool same = true;
+    for (int k = 0; k < ngc; k++) {
+      const GContact &gk = gc[k];
+      for (int rr = 0; rr < 4; rr++) {
+        const float *jt = J[3 * k + 1 + (rr >> 1)], sg = (rr & 1) ? -gk.mu : gk.mu;
+        float z = 0.f;
+        for (int j = 0; j < 14; j++) z += (J[3 * k][j] + sg * jt[j]) * p[j];
+        jp[4 * k + rr] = z;
+        const float now = jar[4 * k + rr], nxt = now + z;
+        // rows that stay within the hysteresis band of the switching surface do not count as a change
+        if ((now < 0.f) != (nxt < 0.f) && fabsf(nxt) > 2e-4f) same = false;
+      }
+    }
+    if (same) { for (int i = 0; i < 14; i++) a[i] += p[i]; break; }
+    if (it >= 40) { nonconv = 1; for (int i = 0; i < 14; i++) a[i] += p[i]; break; }
+    float pMp = 0.f, pg = 0.f;
+    for (int i = 0; i < 14; i++) {
+      float t = 0.f, u = -f[i];
+      for (int j = 0; j < 14; j++) { t += M[i][j] * p[j]; u += M[i][j] * a[j]; }
+      pMp += p[i] * t;
+      pg += p[i] * u;
+    }
+    float lo = 0.f, alpha = 1.f;
+    for (int seg = 0; seg <= nrow; seg++) {
+      float hi = 3.0e38f;                           // next breakpoint above lo
+      for (int r = 0; r < nrow; r++)
+        if (jp[r] != 0.f) { const float t = -jar[r] / jp[r]; if (t > lo && t < hi) hi = t; }
+      const bool last = hi > 1.0e38f;
+      const float mid = last ? lo + 1.f : 0.5f * (lo + hi);
+      float c0 = pg, c1 = pMp;
+      for (int r = 0; r < nrow; r++)
+        if (jar[r] + mid * jp[r] < 0.f) { c0 += Dr[r] * jar[r] * jp[r]; c1 += Dr[r] * jp[r] * jp[r]; }
+      const float root = -c0 / c1;
+      if (last || root <= hi) { alpha = root < lo ? lo : root; break; }
+      lo = hi;
+    }
+    for (int i = 0; i < 14; i++) a[i] += alpha * p[i];
+  }
+  for (int i = 0; i < 14; i++) acc[i] = a[i];
+  return nonconv;
+}
+
+// ------------------------------------------------------------------------------------------------ substep driver
+struct Env03Stats { unsigned coupled, blk_contact, unsupported; };
+
+// gathers every contact of the substep into generic records and runs the coupled solve
+BRB_D int env03_coupled_substep(const BrbModelConsts &c, const Phys &P, const Blk &B, const float (*bpos)[3], const float *bdist,
+                                const float *bn, int nbb, float *acc) {
+  GContact gc[BRB_MAXGC];
+  int n = 0;
+  // wheel-floor contacts of the robot (already set up in P): frame = world axes (n = z, t1 = y, t2 = -x)
+  for (int ci = 0; ci < 4; ci++) {
+    if (!(P.valid & (1u << ci))) continue;
+    GContact &g = gc[n++];
+    g.n[0] = 0.f; g.n[1] = 0.f; g.n[2] = 1.f; g.t1[0] = 0.f; g.t1[1] = 1.f; g.t1[2] = 0.f; g.t2[0] = -1.f; g.t2[1] = 0.f; g.t2[2] = 0.f;
+    for (int k = 0; k < 3; k++) { g.ra[k] = P.cr[ci][k]; g.wa[k] = P.cw[ci][k]; g.rb[k] = 0.f; g.y[k] = P.cy[ci][k]; }
+    g.D = P.cD[ci]; g.mu = c.pp[0][0]; g.robot_sign = 1; g.block_sign = 0; g.wheel = ci >> 1;
+  }
+  for (int k2 = 0; k2 < B.nc; k2++) {
+    GContact &g = gc[n++];
+    g.n[0] = 0.f; g.n[1] = 0.f; g.n[2] = 1.f; g.t1[0] = 0.f; g.t1[1] = 1.f; g.t1[2] = 0.f; g.t2[0] = -1.f; g.t2[1] = 0.f; g.t2[2] = 0.f;
+    for (int k = 0; k < 3; k++) { g.rb[k] = B.cr[k2][k]; g.ra[k] = 0.f; g.wa[k] = 0.f; g.y[k] = B.cy[k2][k]; }
+    g.D = B.cD[k2]; g.mu = c.pp[1][0]; g.robot_sign = 0; g.block_sign = 1; g.wheel = -1;
+  }
+  // chassis-block contacts: body A = robot (chassis), body B = block; normal from chassis to block
+  const float *pp = c.pp[2];
+  const float wr[3] = {P.ex[0] * P.w[0].s + P.ey[0] * P.w[1].s + P.ez[0] * P.w[2].s, P.ex[1] * P.w[0].s + P.ey[1] * P.w[1].s + P.ez[1] * P.w[2].s,
+                       P.ex[2] * P.w[0].s + P.ey[2] * P.w[1].s + P.ez[2] * P.w[2].s};
+  const float wb[3] = {B.ex[0] * B.w[0] + B.ey[0] * B.w[1] + B.ez[0] * B.w[2], B.ex[1] * B.w[0] + B.ey[1] * B.w[1] + B.ez[1] * B.w[2],
+                       B.ex[2] * B.w[0] + B.ey[2] * B.w[1] + B.ez[2] * B.w[2]};
+  const float rp[3] = {P.p[0].s, P.p[1].s, P.p[2].s};
+  for (int k2 = 0; k2 < nbb && n < BRB_MAXGC; k2++) {
+    if (bdist[k2] >= pp[7]) continue;
+    GContact &g = gc[n++];
+    for (int k = 0; k < 3; k++) g.n[k] = bn[k];
+    make_frame3(g.n, g.t1, g.t2);
+    for (int k = 0; k < 3; k++) { g.ra[k] = bpos[k2][k] - rp[k]; g.rb[k] = bpos[k2][k] - B.p[k]; g.wa[k] = 0.f; }
+    const float va[3] = {P.v[0].s + wr[1] * g.ra[2] - wr[2] * g.ra[1], P.v[1].s + wr[2] * g.ra[0] - wr[0] * g.ra[2], P.v[2].s + wr[0] * g.ra[1] - wr[1] * g.ra[0]};
+    const float vb[3] = {B.v[0] + wb[1] * g.rb[2] - wb[2] * g.rb[1], B.v[1] + wb[2] * g.rb[0] - wb[0] * g.rb[2], B.v[2] + wb[0] * g.rb[1] - wb[1] * g.rb[0]};
+    const float dv[3] = {vb[0] - va[0], vb[1] - va[1], vb[2] - va[2]};
+    const float imp = imp_of(pp, bdist[k2]);
+    g.D = pp[3] * imp / (1.f - imp); g.mu = pp[0];
+    g.y[0] = pp[2] * dot3f(g.n, dv) + pp[1] * imp * (bdist[k2] - pp[7]);
+    g.y[1] = pp[2] * dot3f(g.t1, dv);
+    g.y[2] = pp[2] * dot3f(g.t2, dv);
+    g.robot_sign = -1; g.block_sign = 1; g.wheel = -1;
+  }
+  return env03_coupled_solve(c, P, gc, n, acc);
+}
+
+// world-frame smooth force of the robot (phys_setup only fills it when a wheel touches the floor)
+BRB_D void phys_world_force(const BrbModelConsts &c, Phys &P) {
+  const float n0 = P.ex[2], n1 = P.ey[2], n2 = P.ez[2];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    P.f[k] = P.ex[k] * (P.fb[0] + mg_n(c, n0)) + P.ey[k] * (P.fb[1] + mg_n(c, n1)) + P.ez[k] * (P.fb[2] + mg_n(c, n2));
+    P.f[3 + k] = P.ex[k] * P.fb[3] + P.ey[k] * P.fb[4] + P.ez[k] * P.fb[5];
+  }
+  P.f[2] -= c.mass * c.grav;
+  P.f[6] = P.fb[6]; P.f[7] = P.fb[7];
+}
+
+// does the block touch the chassis box this substep?  bounding spheres first, then the SAT collider
+BRB_D int env03_detect(const BrbModelConsts &c, const Phys &P, const Blk &B, float (*bpos)[3], float *bdist, float *bn) {
+  float pc[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) pc[k] = P.p[k].s + P.ex[k] * c.chassis_pos[0] + P.ey[k] * c.chassis_pos[1] + P.ez[k] * c.chassis_pos[2];
+  const float dx = B.p[0] - pc[0], dy = B.p[1] - pc[1], dz = B.p[2] - pc[2];
+  const float reach = c.chassis_radius + c.blk_radius + c.pp[2][7];
+  if (dx * dx + dy * dy + dz * dz > reach * reach) return 0;
+  const float A[3][3] = {{P.ex[0], P.ex[1], P.ex[2]}, {P.ey[0], P.ey[1], P.ey[2]}, {P.ez[0], P.ez[1], P.ez[2]}};
+  const float Bx[3][3] = {{B.ex[0], B.ex[1], B.ex[2]}, {B.ey[0], B.ey[1], B.ey[2]}, {B.ez[0], B.ez[1], B.ez[2]}};
+  const float h2[3] = {c.blk_half, c.blk_half, c.blk_half};
+  return env03_box_box(pc, A, c.chassis_half, B.p, Bx, h2, c.pp[2][7], bpos, bdist, bn);
+}
+
+template <int MAXIT>
+BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&qstale)[4], float (&pstale)[3], Env03Stats &es) {
+  int sidx = 0, it = 0;
+  bool rconv = false, bconv = false;
+  float ra[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ba[6] = {0, 0, 0, 0, 0, 0};
+  float bpos[8][3], bdist[8], bn[3];
+  phys_setup<true>(c, P);
+  blk_setup(c, B);
+  int nbb = env03_detect(c, P, B, bpos, bdist, bn);
+  for (;;) {
+    if (nbb > 0) {
+      float acc[14];
+      if (!P.valid) phys_world_force(c, P);
+      es.coupled++;
+      if (env03_coupled_substep(c, P, B, bpos, bdist, bn, nbb, acc)) P.n_nonconv++;
+      ra[0] = acc[0]; ra[1] = acc[1]; ra[2] = acc[2];
+      ra[3] = P.ex[0] * acc[3] + P.ex[1] * acc[4] + P.ex[2] * acc[5];
+      ra[4] = P.ey[0] * acc[3] + P.ey[1] * acc[4] + P.ey[2] * acc[5];
+      ra[5] = P.ez[0] * acc[3] + P.ez[1] * acc[4] + P.ez[2] * acc[5];
+      ra[6] = acc[6]; ra[7] = acc[7];
+#pragma unroll
+      for (int k = 0; k < 6; k++) ba[k] = acc[8 + k];
+      rconv = bconv = true;
+    } else {
+      if (!rconv) {
+        if (P.valid) {
+          float a[8];
+          phys_solve<true>(c, P, P.bits, a);
+          const unsigned nb = phys_active_set<true>(c, P, a, P.bits);
+          rconv = (nb == P.bits);
+          P.bits = nb;
+          if (!rconv && ++it >= MAXIT) { P.n_nonconv++; rconv = true; }
+          ra[0] = a[0]; ra[1] = a[1]; ra[2] = a[2];
+          ra[3] = P.ex[0] * a[3] + P.ex[1] * a[4] + P.ex[2] * a[5];
+          ra[4] = P.ey[0] * a[3] + P.ey[1] * a[4] + P.ey[2] * a[5];
+          ra[5] = P.ez[0] * a[3] + P.ez[1] * a[4] + P.ez[2] * a[5];
+          ra[6] = a[6]; ra[7] = a[7];
+        } else {
+          const float *f = P.fb;
+          const float u0 = c.minv_xy[0] * f[0] + c.minv_xy[1] * f[4];
+          const float u1 = c.minv_blk[0] * f[1] + c.minv_blk[1] * f[3] + c.minv_blk[2] * f[6] + c.minv_blk[3] * f[7];
+          const float u2 = c.minv_uz * f[2];
+          ra[0] = P.ex[0] * u0 + P.ey[0] * u1 + P.ez[0] * u2;
+          ra[1] = P.ex[1] * u0 + P.ey[1] * u1 + P.ez[1] * u2;
+          ra[2] = P.ex[2] * u0 + P.ey[2] * u1 + P.ez[2] * u2;
+          ra[3] = c.minv_blk[1] * f[1] + c.minv_blk[4] * f[3] + c.minv_blk[5] * f[6] + c.minv_blk[6] * f[7];
+          ra[4] = c.minv_xy[1] * f[0] + c.minv_xy[2] * f[4];
+          ra[5] = c.minv_wz * f[5];
+          ra[6] = c.minv_blk[2] * f[1] + c.minv_blk[5] * f[3] + c.minv_blk[7] * f[6] + c.minv_blk[8] * f[7];
+          ra[7] = c.minv_blk[3] * f[1] + c.minv_blk[6] * f[3] + c.minv_blk[8] * f[6] + c.minv_blk[9] * f[7];
+          rconv = true;
+        }
+      }
+      if (!bconv) {
+        if (B.nc > 0) {
+          blk_solve(c, B, B.bits, ba);
+          const unsigned nb = blk_active_set(c, B, ba, B.bits);
+          bconv = (nb == B.bits);
+          B.bits = nb;
+          if (!bconv && ++it >= 2 * MAXIT) { P.n_nonconv++; bconv = true; }
+        } else {
+          ba[0] = 0.f; ba[1] = 0.f; ba[2] = -c.grav; ba[3] = 0.f; ba[4] = 0.f; ba[5] = 0.f;
+          bconv = true;
+        }
+      }
+    }
+    if (rconv && bconv) {
+      if (sidx == nsub - 1) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) qstale[k] = P.q[k];
+#pragma unroll
+        for (int k = 0; k < 3; k++) pstale[k] = P.p[k].s - P.p[k].c;       // Q1: xpos is one substep stale too
+      }
+      if (B.nc > 0) es.blk_contact++;
+      phys_finalize(c, P, ra[0], ra[1], ra[2], ra[3], ra[4], ra[5], ra[6], ra[7]);
+      blk_finalize(c, B, ba);
+      if (++sidx >= nsub) break;
+      const unsigned was = P.valid;
+      const int wasn = B.nc;
+      phys_setup<true>(c, P);
+      const unsigned fresh = P.valid & ~was;
+      P.bits |= ((fresh & 1u) ? 0xFu : 0u) | ((fresh & 2u) ? 0xF0u : 0u) | ((fresh & 4u) ? 0xF00u : 0u) | ((fresh & 8u) ? 0xF000u : 0u);
+      blk_setup(c, B);
+      if (B.nc != wasn) B.bits = 0xFFFFu;
+      nbb = env03_detect(c, P, B, bpos, bdist, bn);
+      rconv = bconv = false;
+      it = 0;
+    }
+  }
+}
+
+BRB_D double yaw_of(const double q[4]) {   // RobotBaseEnv.py:177-184
+  if (q[0] == 0.0) return 0.0;
+  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  const double w = q[0] / n, x = q[1] / n, y = q[2] / n, z = q[3] / n;
+  return atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z));
+}
+
+// Env03_v2.set_block_pos_vel (env03_v2.py:25-59).  u[0..4] = target x, target z, block x/y/z_rot.
+BRB_D void env03_fire_block(const double robot_pos[3], const double xquat[4], bool attack_front, const double *u, double *bq /*[7]*/,
+                            double *bv /*[3]*/) {
+  double ang = -yaw_of(xquat);
+  if (!attack_front) ang += BRB_PI;
+  double sn, cs;
+  sincos(ang, &sn, &cs);
+  const double bp[3] = {0.3 * sn + robot_pos[0], 0.3 * cs + robot_pos[1], 0.15};
+  const double tg[3] = {(u[0] - 0.5) * 0.02 + robot_pos[0], 0 + robot_pos[1], u[1] * 0.025 + 0.13};
+  double v[3] = {tg[0] - bp[0], tg[1] - bp[1], tg[2] - bp[2]};
+  const double nrm = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+  for (int k = 0; k < 3; k++) { bv[k] = 7.5 * (v[k] / nrm); bq[k] = bp[k]; }
+  const double x_rot = u[2] * 2 * BRB_PI, y_rot = u[3] * 2 * BRB_PI, z_rot = u[4] * 2 * BRB_PI;
+  double sa, ca, sb, cb, sc, cc;
+  sincos(x_rot / 2, &sa, &ca); sincos(y_rot / 2, &sb, &cb); sincos(z_rot / 2, &sc, &cc);
+  bq[3] = sa * cb * cc - ca * sb * sc;      // scalar-last quaternion into scalar-first slots, as for the robot (Q3)
+  bq[4] = ca * sb * cc + sa * cb * sc;
+  bq[5] = ca * cb * sc - sa * sb * cc;
+  bq[6] = ca * cb * cc + sa * sb * sc;
+}
+
+BRB_D bool env03_attack_front(const BrbState &S, long long i) {   // env03_v2.py:22: np.random.random() > 0.5, once per env
+  double u[4];
+  draw4(S.seed, (uint64_t)(S.env0 + i), 0xFFFFFFFFu, 0u, u);
+  return u[0] > 0.5;
+}
+
+// Env03.reset_model (env03_v1.py:60-83) with Env03_v2.set_block_pos_vel; u[32]: 16 jitter, 3 robot rotation, 5 block draws
+BRB_D void reset_env03(const BrbState &S, long long i, const double *u, float o[6]) {
+  const long long N = S.n;
+  double qpos[16];
+  const double qpos0[16] = {0, 0, 0, 1, 0, 0, 0, 0, 0, 0, 0, 0, 1, 0, 0, 0};
+  for (int k = 0; k < 16; k++) qpos[k] = qpos0[k] + (-0.01 + (0.01 - -0.01) * u[k]);
+  qpos[2] = 0;
+  const double x_rot = (u[16] - 0.5) * 2 * BRB_PI, y_rot = (u[17] - 0.5) * 0.4, z_rot = (u[18] - 0.5) * 0.4;
+  double sa, ca, sb, cb, sc, cc;
+  sincos(x_rot / 2, &sa, &ca); sincos(y_rot / 2, &sb, &cb); sincos(z_rot / 2, &sc, &cc);
+  qpos[3] = sa * cb * cc - ca * sb * sc;
+  qpos[4] = ca * sb * cc + sa * cb * sc;
+  qpos[5] = ca * cb * sc - sa * sb * cc;
+  qpos[6] = ca * cb * cc + sa * sb * sc;
+  double xq[4];
+  const double n = sqrt(qpos[3] * qpos[3] + qpos[4] * qpos[4] + qpos[5] * qpos[5] + qpos[6] * qpos[6]);
+  for (int k = 0; k < 4; k++) { xq[k] = qpos[3 + k] / n; S.xquat[k * N + i] = xq[k]; }
+  double bv[3];
+  env03_fire_block(qpos, xq, env03_attack_front(S, i), u + 19, qpos + 9, bv);     // set_state ran mj_forward: xpos/xquat fresh
+  for (int k = 0; k < 16; k++) S.qpos[k * N + i] = qpos[k];
+  for (int k = 0; k < 14; k++) S.qvel[k * N + i] = 0.0;
+  for (int k = 0; k < 3; k++) S.qvel[(8 + k) * N + i] = bv[k];
+  S.aset[i] = 0xFFFFu;
+  S.v3[0 * N + i] = -1.0;          // block_delay_time_start = None
+  S.v3[2 * N + i] = 65535.0;       // block active set
+  S.elapsed[i] = 0;
+  S.ep_return[i] = 0.0;
+  S.ep_len[i] = 0;
+  const double p = pitch_of(xq);
+  S.last_pitch[i] = p;
+  obs_of(p, 0.0, 0.0, 0.0, 0.0, 0.0, o);
+}
+
+// One VecEnv.step of Env03-v2 for env i (Env03.step, env03_v1.py:26-58).  replay_u row = 8 re-fire slots + 32 reset slots.
+BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long long i, const float *__restrict__ actions,
+                      float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done,
+                      uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs, float *__restrict__ ep_return_out,
+                      int32_t *__restrict__ ep_len_out, const double *__restrict__ replay_u, unsigned stat[10]) {
+  const long long N = S.n;
+  double qvel[14], xq[4];
+  for (int k = 0; k < 14; k++) qvel[k] = S.qvel[k * N + i];
+  for (int k = 0; k < 4; k++) xq[k] = S.xquat[k * N + i];
+  const uint32_t event = S.event[i] + 1u;
+  S.event[i] = event;
+  int elapsed = S.elapsed[i];
+  const double rew = reward_of<BRB_ENV01_V1>(pitch_of(xq), qvel[6], qvel[7], qvel[5], 0.0, 0.0);   // RobotBaseEnv._get_reward
+  const double ctrl[2] = {qvel[6] + (double)actions[2 * i] * 4.0, qvel[7] + (double)actions[2 * i + 1] * 4.0};
+
+  Phys st;
+  Blk B;
+  {
+    double qn[4], nn = 0;
+    for (int k = 0; k < 4; k++) { qn[k] = S.qpos[(3 + k) * N + i]; nn += qn[k] * qn[k]; }
+    nn = 1.0 / sqrt(nn);
+    for (int k = 0; k < 4; k++) st.q[k] = ksplit(qn[k] * nn);
+    for (int k = 0; k < 3; k++) { st.p[k] = ksplit(S.qpos[k * N + i]); st.v[k] = ksplit(qvel[k]); st.w[k] = ksplit(qvel[3 + k]); }
+    for (int k = 0; k < 2; k++) {
+      st.th[k] = ksplit(S.qpos[(7 + k) * N + i]);
+      st.s[k] = ksplit(qvel[6 + k]);
+      const double u = fmin((double)c.ctrl_hi, fmax((double)c.ctrl_lo, ctrl[k]));
+      st.uhi[k] = (float)u;
+      st.ulo[k] = (float)(u - (double)st.uhi[k]);
+    }
+    st.bits = S.aset[i];
+    st.n_contact = st.n_solve = st.n_nonconv = st.n_slots = 0;
+    nn = 0;
+    for (int k = 0; k < 4; k++) { qn[k] = S.qpos[(12 + k) * N + i]; nn += qn[k] * qn[k]; }
+    nn = 1.0 / sqrt(nn);
+    for (int k = 0; k < 4; k++) B.q[k] = (float)(qn[k] * nn);
+    for (int k = 0; k < 3; k++) { B.p[k] = (float)S.qpos[(9 + k) * N + i]; B.v[k] = (float)qvel[8 + k]; B.w[k] = (float)qvel[11 + k]; }
+    B.bits = (unsigned)S.v3[2 * N + i];
+    B.nc = 0;
+  }
+  KF qprev[4];
+  float pstale[3];
+  Env03Stats es = {0u, 0u, 0u};
+  phys03_run<BRB_MAXIT>(c, st, B, c.frame_skip, qprev, pstale, es);
+  stat[0] = c.frame_skip; stat[1] = st.n_contact; stat[2] = st.n_solve; stat[3] = st.n_nonconv; stat[7] = st.n_slots;
+  stat[8] = es.coupled; stat[9] = es.blk_contact;
+  {
+    const float drop = 0.005f * (fabsf(st.v[2].s) + 0.12f * (fabsf(st.w[0].s) + fabsf(st.w[1].s) + fabsf(st.w[2].s))) + 0.0005f;
+    const bool far = phys_clearance(c, st) > drop;
+    stat[6] = (st.valid == 0u && far) ? 0u : 1u + group_rank(st.valid);
+    // robots whose block is (or will be within one step) inside the chassis' reach go through the slow coupled solve:
+    // give them their own bucket so they do not stall warps of robots on the fast path
+    const float dx = B.p[0] - st.p[0].s, dy = B.p[1] - st.p[1].s, dz = B.p[2] - (st.p[2].s + c.chassis_pos[2]);
+    const float reach = c.chassis_radius + c.blk_radius + 0.06f;
+    if (dx * dx + dy * dy + dz * dz < reach * reach) stat[6] = BRB_NGROUPS - 1;
+  }
+
+  double qpos[16];
+  for (int k = 0; k < 3; k++) { qpos[k] = kjoin(st.p[k]); qvel[k] = kjoin(st.v[k]); qvel[3 + k] = kjoin(st.w[k]); }
+  for (int k = 0; k < 4; k++) qpos[3 + k] = kjoin(st.q[k]);
+  for (int k = 0; k < 2; k++) { qpos[7 + k] = kjoin(st.th[k]); qvel[6 + k] = kjoin(st.s[k]); }
+  for (int k = 0; k < 3; k++) { qpos[9 + k] = (double)B.p[k]; qvel[8 + k] = (double)B.v[k]; qvel[11 + k] = (double)B.w[k]; }
+  for (int k = 0; k < 4; k++) qpos[12 + k] = (double)B.q[k];
+  {
+    double nn = 0;
+    for (int k = 0; k < 4; k++) { xq[k] = kjoin(qprev[k]); nn += xq[k] * xq[k]; }
+    nn = 1.0 / sqrt(nn);
+    for (int k = 0; k < 4; k++) xq[k] *= nn;
+  }
+  elapsed += 1;
+  const double tnow = S.time_table[elapsed];
+  // block logic (env03_v1.py:39-49): remove a block that came to rest, re-fire it 0.5 s later
+  double timer = S.v3[0 * N + i];
+  {
+    const double bs = sqrt(qvel[8] * qvel[8] + qvel[9] * qvel[9] + qvel[10] * qvel[10]);
+    if (bs < 0.1 && timer < 0.0) { qpos[9] = 10; qpos[10] = 10; qpos[11] = 0; timer = tnow; }
+    if (timer >= 0.0 && (tnow - timer) > 0.5) {
+      double uf[8];
+      if (replay_u) { for (int k = 0; k < 8; k++) uf[k] = replay_u[i * 40 + k]; }
+      else { draw4(S.seed, (uint64_t)(S.env0 + i), event, 9u, uf); draw4(S.seed, (uint64_t)(S.env0 + i), event, 10u, uf + 4); }
+      const double rp[3] = {(double)pstale[0], (double)pstale[1], (double)pstale[2]};
+      double bv[3];
+      env03_fire_block(rp, xq, env03_attack_front(S, i), uf, qpos + 9, bv);
+      for (int k = 0; k < 3; k++) qvel[8 + k] = bv[k];
+      timer = -1.0;
+    }
+  }
+  const double p_true = pitch_of(xq);
+  const bool terminated = fabs(p_true) > (50 * BRB_PI / 180);
+  const bool trunc = elapsed >= c.max_episode_steps;
+  const double dt = tnow - S.time_table[elapsed - 1];
+  double pitch_dot = 0.0;
+  if (dt > 0.0) pitch_dot = (p_true - S.last_pitch[i]) / dt;
+  float o[6];
+  obs_of(p_true, pitch_dot, qvel[6], qvel[7], 0.0, 0.0, o);
+  const double epr = S.ep_return[i] + rew;
+  const int epl = S.ep_len[i] + 1;
+  const bool dn = terminated || trunc;
+  if (reward) reward[i] = (float)rew;
+  if (done) done[i] = (uint8_t)dn;
+  if (truncated) truncated[i] = (uint8_t)(trunc && !terminated);
+  if (ep_return_out) ep_return_out[i] = (float)epr;
+  if (ep_len_out) ep_len_out[i] = epl;
+  stat[4] = es.unsupported ? 1u : 0u;
+  if (dn) {
+    stat[5] = 1;
+    stat[6] = 0;
+    if (terminal_obs) for (int k = 0; k < 6; k++) terminal_obs[i * 6 + k] = o[k];
+    double ur[32];
+    if (replay_u) { for (int k = 0; k < 32; k++) ur[k] = replay_u[i * 40 + 8 + k]; }
+    else { for (int b = 0; b < 8; b++) draw4(S.seed, (uint64_t)(S.env0 + i), event, 1u + b, ur + 4 * b); }
+    reset_env03(S, i, ur, o);
+  } else {
+    for (int k = 0; k < 16; k++) S.qpos[k * N + i] = qpos[k];
+    for (int k = 0; k < 14; k++) S.qvel[k * N + i] = qvel[k];
+    for (int k = 0; k < 4; k++) S.xquat[k * N + i] = xq[k];
+    S.aset[i] = st.bits;
+    S.v3[0 * N + i] = timer;
+    S.v3[2 * N + i] = (double)B.bits;
+    S.elapsed[i] = elapsed;
+    S.last_pitch[i] = p_true;
+    S.ep_return[i] = epr;
+    S.ep_len[i] = epl;
+  }
+  for (int k = 0; k < 6; k++) obs[i * 6 + k] = o[k];
+}
+#endif

@@ -15,15 +15,17 @@
 // envs read 32 consecutive values of every column (fully coalesced 256 B / 128 B segments).
 struct BrbState {
   long long n;            // envs in this shard
+  int nq, nv;             // 9, 8 (Env01-*) or 16, 14 (Env03-v2: + free block)
   long long env0;         // global id of env 0 (Philox counter)
   unsigned long long seed;
-  double *qpos;           // [9][N]  x y z qw qx qy qz thL thR        (MuJoCo data.qpos)
-  double *qvel;           // [8][N]  v_world(3) w_body(3) sL sR       (MuJoCo data.qvel)
+  double *qpos;           // [nq][N] x y z qw qx qy qz thL thR [block x y z qw qx qy qz]   (MuJoCo data.qpos)
+  double *qvel;           // [nv][N] v_world(3) w_body(3) sL sR [block v_world(3) w_body(3)] (MuJoCo data.qvel)
   double *xquat;          // [4][N]  chassis quaternion as the task logic sees it (one substep stale, Q1)
   uint32_t *aset;         // [N]     converged contact-row active set of the last substep (the solver's warm start)
   double *last_pitch;     // [N]     RobotBaseEnv.last_pitch
   double *ep_return;      // [N]     Monitor running return
-  double *v3;             // [3][N]  target_wheel_speed, delay_target_speed, pitch_offset (Env01-v3 only)
+  double *v3;             // [3][N]  Env01-v3: target_wheel_speed, delay_target_speed, pitch_offset;
+                          //         Env03-v2: block timer start (<0 = none), attack_side_front, block active-set bits
   int *elapsed;           // [N]     TimeLimit._elapsed_steps (also indexes the time table)
   int *ep_len;            // [N]
   uint32_t *event;        // [N]     Philox event counter (0 = reset_all, k = k-th step call)

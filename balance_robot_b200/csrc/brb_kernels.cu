@@ -207,13 +207,22 @@ struct Phys {
   float f[8];                               // smooth force: world linear (3), world angular (3), wheels (2)
   float fb[8];                              // the same in the chassis frame (free-flight path: a_b = M_b^-1 f_b)
   float cr[4][3], cw[4][3], cy[4][3];       // per contact: r_w (from the chassis origin), wheel column w_w, yhat (n, t1, t2)
+  float cD[4];                              // per-contact row weight D (only with position-dependent impedance: Env03-v2)
   unsigned valid;                           // bit ci: contact slot ci (2*wheel + rim end) is in contact
   bool clampL, clampR;                      // servo sits on its forcerange (A.9)
   unsigned n_contact, n_solve, n_nonconv, n_slots;
 };
 
 // ---- A.3 steps 2-7: kinematics, smooth forces, collision, reference accelerations
-template <int CI>
+// impedance imp(dist) of a dynamic pair (solimp midpoint 0.5, power 2).  pp = {mu, K, B, D1, d0, d1, width, margin}
+BRB_D float imp_of(const float *pp, float dist) {
+  const float x = fabsf(dist - pp[7]) / pp[6];
+  if (x >= 1.f) return pp[5];
+  const float y = (x <= 0.5f) ? 2.f * x * x : 1.f - 2.f * (1.f - x) * (1.f - x);
+  return pp[4] + y * (pp[5] - pp[4]);
+}
+
+template <int CI, bool VI>
 BRB_D void contact_setup(const BrbModelConsts &c, Phys &P, float d0, float anx, float sa, const float (&G)[3], const float (&A)[3],
                          const float (&B2)[3], const float (&ww)[3]) {
   constexpr int k = CI >> 1, e = CI & 1;
@@ -233,12 +242,21 @@ BRB_D void contact_setup(const BrbModelConsts &c, Phys &P, float d0, float anx, 
     const float pz = P.v[2].s + ww[0] * ry - ww[1] * rx + sk * wz;
     P.cr[CI][0] = rx; P.cr[CI][1] = ry; P.cr[CI][2] = rz;
     P.cw[CI][0] = wx; P.cw[CI][1] = wy; P.cw[CI][2] = wz;
-    P.cy[CI][0] = c.Bdamp * pz + c.Kimp * dist;
-    P.cy[CI][1] = c.Bdamp * py;
-    P.cy[CI][2] = -c.Bdamp * px;
+    if (VI) {
+      const float imp = imp_of(c.pp[0], dist);
+      P.cD[CI] = c.pp[0][3] * imp / (1.f - imp);
+      P.cy[CI][0] = c.pp[0][2] * pz + c.pp[0][1] * imp * dist;
+      P.cy[CI][1] = c.pp[0][2] * py;
+      P.cy[CI][2] = -c.pp[0][2] * px;
+    } else {
+      P.cy[CI][0] = c.Bdamp * pz + c.Kimp * dist;
+      P.cy[CI][1] = c.Bdamp * py;
+      P.cy[CI][2] = -c.Bdamp * px;
+    }
   }
 }
 
+template <bool VI = false>
 BRB_D void phys_setup(const BrbModelConsts &c, Phys &P) {
   const float qw = P.q[0].s, qx = P.q[1].s, qy = P.q[2].s, qz = P.q[3].s;
   const float xx = qx * qx, yy = qy * qy, zz = qz * qz, xy = qx * qy, xz = qx * qz, yz = qy * qz, wx = qw * qx, wy = qw * qy, wz = qw * qz;
@@ -298,10 +316,10 @@ BRB_D void phys_setup(const BrbModelConsts &c, Phys &P) {
       ww[k] = P.ex[k] * w0 + P.ey[k] * w1 + P.ez[k] * w2;        // world angular velocity
     }
     const float dL0 = common - c.ox * n0, dR0 = common + c.ox * n0;
-    contact_setup<0>(c, P, dL0, anx, sa, G, A, B2, ww);
-    contact_setup<1>(c, P, dL0, anx, sa, G, A, B2, ww);
-    contact_setup<2>(c, P, dR0, anx, sa, G, A, B2, ww);
-    contact_setup<3>(c, P, dR0, anx, sa, G, A, B2, ww);
+    contact_setup<0, VI>(c, P, dL0, anx, sa, G, A, B2, ww);
+    contact_setup<1, VI>(c, P, dL0, anx, sa, G, A, B2, ww);
+    contact_setup<2, VI>(c, P, dR0, anx, sa, G, A, B2, ww);
+    contact_setup<3, VI>(c, P, dR0, anx, sa, G, A, B2, ww);
   }
   if (P.valid) { P.n_contact++; P.n_slots += __popc(P.valid); }
 }
@@ -310,7 +328,7 @@ BRB_D void phys_setup(const BrbModelConsts &c, Phys &P) {
 // Rows within `eps` of the switching surface keep their previous state (`prev`): either choice gives the same
 // force to O(D*eps) ~ 2e-5 N, and without the hysteresis fp32 noise can flip such a row back and forth forever.
 template <int CI>
-BRB_D unsigned contact_bits(const BrbModelConsts &c, const Phys &P, const float (&a)[8], unsigned prev) {
+BRB_D unsigned contact_bits(const BrbModelConsts &c, const Phys &P, const float (&a)[8], unsigned prev, float mu) {
   if (!(P.valid & (1u << CI))) return 0u;
   const float ak = a[6 + (CI >> 1)];
   const float rx = P.cr[CI][0], ry = P.cr[CI][1], rz = P.cr[CI][2];
@@ -318,28 +336,31 @@ BRB_D unsigned contact_bits(const BrbModelConsts &c, const Phys &P, const float 
   const float py = a[1] + a[5] * rx - a[3] * rz + ak * P.cw[CI][1];
   const float pz = a[2] + a[3] * ry - a[4] * rx + ak * P.cw[CI][2];
   const float z0 = pz + P.cy[CI][0];
-  const float z1 = c.mu * (py + P.cy[CI][1]);
-  const float z2 = c.mu * (P.cy[CI][2] - px);
+  const float z1 = mu * (py + P.cy[CI][1]);
+  const float z2 = mu * (P.cy[CI][2] - px);
   const float eps = 2e-4f;
   const unsigned pb = prev >> (4 * CI);
   const float e0 = (pb & 1u) ? eps : -eps, e1 = (pb & 2u) ? eps : -eps, e2 = (pb & 4u) ? eps : -eps, e3 = (pb & 8u) ? eps : -eps;
   return ((unsigned)(z0 + z1 < e0) | ((unsigned)(z0 - z1 < e1) << 1) | ((unsigned)(z0 + z2 < e2) << 2) | ((unsigned)(z0 - z2 < e3) << 3)) << (4 * CI);
 }
 
+template <bool VI = false>
 BRB_D unsigned phys_active_set(const BrbModelConsts &c, const Phys &P, const float (&a)[8], unsigned prev) {
-  return contact_bits<0>(c, P, a, prev) | contact_bits<1>(c, P, a, prev) | contact_bits<2>(c, P, a, prev) | contact_bits<3>(c, P, a, prev);
+  const float mu = VI ? c.pp[0][0] : c.mu;
+  return contact_bits<0>(c, P, a, prev, mu) | contact_bits<1>(c, P, a, prev, mu) | contact_bits<2>(c, P, a, prev, mu) | contact_bits<3>(c, P, a, prev, mu);
 }
 
 // ---- H += P_c' S P_c, r -= P_c' S yhat-ish for one contact; S = Pi' W_c Pi in world axes:
 //      Sxx = W22, Syy = W11, Szz = W00, Syz = W01, Sxz = -W02, Sxy = 0
-template <int CI>
+template <int CI, bool VI>
 BRB_D void contact_assemble(const BrbModelConsts &c, const Phys &P, unsigned bits, float (&H)[36], float (&r)[8]) {
   const unsigned b = (bits >> (4 * CI)) & 15u;
   if ((P.valid & (1u << CI)) && b) {
     constexpr int kw = 6 + (CI >> 1);
     const float b0 = (float)(b & 1u), b1 = (float)((b >> 1) & 1u), b2 = (float)((b >> 2) & 1u), b3 = (float)((b >> 3) & 1u);
-    const float Dm = c.D * c.mu, Dmm = Dm * c.mu;
-    const float Szz = c.D * (b0 + b1 + b2 + b3), Syz = Dm * (b0 - b1), Sxz = -Dm * (b2 - b3);
+    const float Dc = VI ? P.cD[CI] : c.D, muc = VI ? c.pp[0][0] : c.mu;
+    const float Dm = Dc * muc, Dmm = Dm * muc;
+    const float Szz = Dc * (b0 + b1 + b2 + b3), Syz = Dm * (b0 - b1), Sxz = -Dm * (b2 - b3);
     const float Syy = Dmm * (b0 + b1), Sxx = Dmm * (b2 + b3);
     const float rx = P.cr[CI][0], ry = P.cr[CI][1], rz = P.cr[CI][2];
     const float wx = P.cw[CI][0], wy = P.cw[CI][1], wz = P.cw[CI][2];
@@ -375,6 +396,7 @@ BRB_D void contact_assemble(const BrbModelConsts &c, const Phys &P, unsigned bit
 }
 
 // ---- one Newton step on the active set `bits`: (M' + sum P'SP) a = f - sum P'S yhat   (A.8; exact for a fixed set)
+template <bool VI = false>
 BRB_D void phys_solve(const BrbModelConsts &c, Phys &P, unsigned bits, float (&a)[8]) {
   float H[36], r[8];
 #pragma unroll
@@ -401,10 +423,10 @@ BRB_D void phys_solve(const BrbModelConsts &c, Phys &P, unsigned bits, float (&a
   }
 #pragma unroll
   for (int k = 0; k < 8; k++) r[k] = P.f[k];
-  contact_assemble<0>(c, P, bits, H, r);
-  contact_assemble<1>(c, P, bits, H, r);
-  contact_assemble<2>(c, P, bits, H, r);
-  contact_assemble<3>(c, P, bits, H, r);
+  contact_assemble<0, VI>(c, P, bits, H, r);
+  contact_assemble<1, VI>(c, P, bits, H, r);
+  contact_assemble<2, VI>(c, P, bits, H, r);
+  contact_assemble<3, VI>(c, P, bits, H, r);
   // Cholesky H = L L' and the two triangular solves, straight-line (generated: gen_chol8.py)
 #include "brb_chol8.inc"
 #pragma unroll
@@ -551,7 +573,7 @@ template <int KIND>
 BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long i, const float *__restrict__ actions,
                     float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done,
                     uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs, float *__restrict__ ep_return_out,
-                    int32_t *__restrict__ ep_len_out, const double *__restrict__ replay_u, unsigned stat[8]) {
+                    int32_t *__restrict__ ep_len_out, const double *__restrict__ replay_u, unsigned stat[10]) {
   const long long N = S.n;
   // ---------------- prologue (fp64 task logic on the pre-step state) ----------------
   double qvel[8], xq[4];
@@ -605,7 +627,6 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
       st.uhi[k] = (float)u;
       st.ulo[k] = (float)(u - (double)st.uhi[k]);
     }
-#pragma unroll
     st.bits = S.aset[i];
     st.n_contact = st.n_solve = st.n_nonconv = st.n_slots = 0;
   }
@@ -702,6 +723,8 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
   for (int k = 0; k < 6; k++) obs[i * 6 + k] = o[k];
 }
 
+#include "brb_env03.cuh"
+
 #ifndef BRB_HOST_EMU
 #ifdef BRB_MAXNREG
 #define BRB_STEP_BOUNDS __maxnreg__(BRB_MAXNREG)
@@ -720,8 +743,11 @@ __global__ void BRB_STEP_BOUNDS brb_step_kernel(const __grid_constant__ BrbModel
   // envs are visited in the order of the partition built by the previous step: robots expected to stay airborne
   // first, grounded ones last, so a warp's lanes mostly run the same path (state columns are addressed by env id)
   const long long i = live ? (perm.in ? (long long)perm.in[tid] : tid) : 0;
-  unsigned stat[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-  if (live) step_env<KIND>(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat);
+  unsigned stat[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  if (live) {
+    if (KIND == BRB_ENV03_V2) step_env03(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat);
+    else step_env<KIND>(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat);
+  }
   if (perm.key_out) {
     // publish this robot's group key and add it to the histogram the grouping kernel turns into bucket offsets
     const unsigned key = live ? stat[6] : 31u;
@@ -731,7 +757,8 @@ __global__ void BRB_STEP_BOUNDS brb_step_kernel(const __grid_constant__ BrbModel
   }
   // statistics: one atomic per warp per counter
   const unsigned long long a0 = warp_sum(stat[0]), a1 = warp_sum(stat[1]), a2 = warp_sum(stat[2]), a3 = warp_sum(stat[3]),
-                           a4 = warp_sum(stat[4]), a5 = warp_sum(stat[5]), a6 = warp_sum(live ? 1u : 0u), a7 = warp_sum(stat[7]);
+                           a4 = warp_sum(stat[4]), a5 = warp_sum(stat[5]), a6 = warp_sum(live ? 1u : 0u), a7 = warp_sum(stat[7]),
+                           stat8 = warp_sum(stat[8]), stat9 = warp_sum(stat[9]);
   if ((threadIdx.x & 31) == 0) {
     atomicAdd(&S.stats[BRB_STAT_SUBSTEPS], a0);
     atomicAdd(&S.stats[BRB_STAT_CONTACT_SUBSTEPS], a1);
@@ -741,6 +768,11 @@ __global__ void BRB_STEP_BOUNDS brb_step_kernel(const __grid_constant__ BrbModel
     if (a5) atomicAdd(&S.stats[BRB_STAT_EPISODES], a5);
     atomicAdd(&S.stats[BRB_STAT_ENV_STEPS], a6);
     atomicAdd(&S.stats[BRB_STAT_CONTACT_SLOTS], a7);
+    if (KIND == BRB_ENV03_V2) {
+      const unsigned long long a8 = stat8, a9 = stat9;
+      if (a8) atomicAdd(&S.stats[BRB_STAT_COUPLED_SUBSTEPS], a8);
+      if (a9) atomicAdd(&S.stats[BRB_STAT_BLOCK_CONTACT_SUBSTEPS], a9);
+    }
   }
 }
 
@@ -767,17 +799,24 @@ template <int KIND>
 __global__ void brb_reset_kernel(const BrbState S, float *__restrict__ obs, const double *__restrict__ replay_u) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S.n) return;
-  double ur[16];
-  if (replay_u) {
-#pragma unroll
-    for (int k = 0; k < 16; k++) ur[k] = replay_u[i * 16 + k];
-  } else {
-#pragma unroll
-    for (int b = 0; b < 4; b++) draw4(S.seed, (uint64_t)(S.env0 + i), 0u, 1u + b, ur + 4 * b);
-  }
   S.event[i] = 0u;
   float o[6];
-  reset_env<KIND>(S, i, ur, o);
+  if (KIND == BRB_ENV03_V2) {
+    double ur[32];
+    if (replay_u) { for (int k = 0; k < 32; k++) ur[k] = replay_u[i * 32 + k]; }
+    else { for (int b = 0; b < 8; b++) draw4(S.seed, (uint64_t)(S.env0 + i), 0u, 1u + b, ur + 4 * b); }
+    reset_env03(S, i, ur, o);
+  } else {
+    double ur[16];
+    if (replay_u) {
+#pragma unroll
+      for (int k = 0; k < 16; k++) ur[k] = replay_u[i * 16 + k];
+    } else {
+#pragma unroll
+      for (int b = 0; b < 4; b++) draw4(S.seed, (uint64_t)(S.env0 + i), 0u, 1u + b, ur + 4 * b);
+    }
+    reset_env<KIND>(S, i, ur, o);
+  }
 #pragma unroll
   for (int k = 0; k < 6; k++) obs[i * 6 + k] = o[k];
 }
@@ -785,8 +824,8 @@ __global__ void brb_reset_kernel(const BrbState S, float *__restrict__ obs, cons
 __global__ void brb_get_state_kernel(const BrbState S, double *qpos, double *qvel, double *xquat) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S.n) return;
-  if (qpos) for (int k = 0; k < 9; k++) qpos[i * 9 + k] = S.qpos[k * S.n + i];
-  if (qvel) for (int k = 0; k < 8; k++) qvel[i * 8 + k] = S.qvel[k * S.n + i];
+  if (qpos) for (int k = 0; k < S.nq; k++) qpos[i * S.nq + k] = S.qpos[k * S.n + i];
+  if (qvel) for (int k = 0; k < S.nv; k++) qvel[i * S.nv + k] = S.qvel[k * S.n + i];
   if (xquat) for (int k = 0; k < 4; k++) xquat[i * 4 + k] = S.xquat[k * S.n + i];
 }
 
@@ -794,13 +833,13 @@ __global__ void brb_get_state_kernel(const BrbState S, double *qpos, double *qve
 __global__ void brb_set_state_kernel(const BrbState S, const double *qpos, const double *qvel) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S.n) return;
-  for (int k = 0; k < 9; k++) S.qpos[k * S.n + i] = qpos[i * 9 + k];
-  for (int k = 0; k < 8; k++) S.qvel[k * S.n + i] = qvel[i * 8 + k];
+  for (int k = 0; k < S.nq; k++) S.qpos[k * S.n + i] = qpos[i * S.nq + k];
+  for (int k = 0; k < S.nv; k++) S.qvel[k * S.n + i] = qvel[i * S.nv + k];
   S.aset[i] = 0xFFFFu;
   double nn = 0;
-  for (int k = 0; k < 4; k++) nn += qpos[i * 9 + 3 + k] * qpos[i * 9 + 3 + k];
+  for (int k = 0; k < 4; k++) nn += qpos[i * S.nq + 3 + k] * qpos[i * S.nq + 3 + k];
   nn = 1.0 / sqrt(nn);
-  for (int k = 0; k < 4; k++) S.xquat[k * S.n + i] = qpos[i * 9 + 3 + k] * nn;
+  for (int k = 0; k < 4; k++) S.xquat[k * S.n + i] = qpos[i * S.nq + 3 + k] * nn;
 }
 
 __global__ void brb_get_elapsed_kernel(const BrbState S, int32_t *out) {
@@ -834,8 +873,11 @@ extern "C" void brb_launch_step(int kind, const BrbModelConsts *c, const BrbStat
     case BRB_ENV01_V2:
       brb_step_kernel<BRB_ENV01_V2><<<grid, BRB_BLOCK, 0, stream>>>(*c, *S, *perm, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
       break;
-    default:
+    case BRB_ENV01_V3:
       brb_step_kernel<BRB_ENV01_V3><<<grid, BRB_BLOCK, 0, stream>>>(*c, *S, *perm, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
+      break;
+    default:
+      brb_step_kernel<BRB_ENV03_V2><<<grid, BRB_BLOCK, 0, stream>>>(*c, *S, *perm, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
       break;
   }
 }
@@ -854,7 +896,8 @@ extern "C" void brb_launch_reset(int kind, const BrbState *S, float *obs, const 
   switch (kind) {
     case BRB_ENV01_V1: brb_reset_kernel<BRB_ENV01_V1><<<grid, 128, 0, stream>>>(*S, obs, replay_u); break;
     case BRB_ENV01_V2: brb_reset_kernel<BRB_ENV01_V2><<<grid, 128, 0, stream>>>(*S, obs, replay_u); break;
-    default: brb_reset_kernel<BRB_ENV01_V3><<<grid, 128, 0, stream>>>(*S, obs, replay_u); break;
+    case BRB_ENV01_V3: brb_reset_kernel<BRB_ENV01_V3><<<grid, 128, 0, stream>>>(*S, obs, replay_u); break;
+    default: brb_reset_kernel<BRB_ENV03_V2><<<grid, 128, 0, stream>>>(*S, obs, replay_u); break;
   }
 }
 

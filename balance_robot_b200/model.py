@@ -49,6 +49,10 @@ class BrbModelConsts(C.Structure):
         ("impl_W", C.c_float * 8), ("impl_G", C.c_float * 3), ("impl_cinv_full", C.c_float), ("impl_cinv_damp", C.c_float),
         ("chassis_half", C.c_float * 3), ("chassis_pos", C.c_float * 3),
         ("frame_skip", C.c_int), ("max_episode_steps", C.c_int), ("env_kind", C.c_int), ("flags", C.c_int),
+        ("pp", C.c_float * 8 * 3),
+        ("blk_half", C.c_float), ("blk_mass", C.c_float), ("blk_inertia", C.c_float), ("blk_radius", C.c_float),
+        ("chassis_radius", C.c_float),
+        ("nq", C.c_int), ("nv", C.c_int), ("reserved", C.c_int),
     ]
 
 
@@ -82,13 +86,18 @@ def compile_model(spec: ModelSpec, env_kind: int, max_episode_steps: int, frame_
     if not free_roots:
         raise UnsupportedModel("no free-joint chassis")
     chassis = free_roots[0]
+    block = None
     if len(free_roots) > 1:
-        raise UnsupportedModel("extra free bodies (Env03 block) are not in the CUDA kernel yet")
+        if env_kind != 3 or len(free_roots) != 2:
+            raise UnsupportedModel("a second free body is only supported as the Env03-v2 block")
+        block = free_roots[1]
     if spec.joints[spec.bodies[chassis].joint].dofadr != 0:
         raise UnsupportedModel("chassis free joint must own dofs 0..5")
     wheels = [b for b in range(1, len(spec.bodies)) if spec.bodies[b].parent == chassis]
-    if len(wheels) != 2 or spec.nv != 8 or spec.nq != 9:
+    if len(wheels) != 2 or (spec.nv, spec.nq) != ((8, 9) if block is None else (14, 16)):
         raise UnsupportedModel("expected exactly two hinge wheels on the chassis")
+    if env_kind == 3 and block is None:
+        raise UnsupportedModel("Env03-v2 needs the block scene")
     if tuple(spec.gravity[:2]) != (0.0, 0.0) or spec.gravity[2] >= 0:
         raise UnsupportedModel("gravity must be (0, 0, -g)")
     cb = spec.bodies[chassis]
@@ -181,10 +190,10 @@ def compile_model(spec: ModelSpec, env_kind: int, max_episode_steps: int, frame_
         raise UnsupportedModel("wheel-floor pairs must be condim 3, zero margin/gap, isotropic friction")
     if np.abs(quat_to_mat(floor.quat) - np.eye(3)).max() > 1e-12 or floor.pos[0] != 0 or floor.pos[1] != 0:
         raise UnsupportedModel("floor must be a z-up plane")
-    d0, d1, width = (min(0.9999, max(0.0001, x)) for x in p0.solimp[:3])
-    if d0 != d1:
-        raise UnsupportedModel("position-dependent impedance (solimp d0 != dmax) is not in the CUDA kernel yet")
-    imp = 0.5 * (d0 + d1)
+    d0, d1 = (min(0.9999, max(0.0001, x)) for x in p0.solimp[:2])
+    if d0 != d1 and block is None:
+        raise UnsupportedModel("position-dependent impedance (solimp d0 != dmax) is only built into the Env03-v2 kernel")
+    imp = 0.5 * (d0 + d1) if d0 == d1 else d1     # Env03-v2 evaluates imp(dist) per contact (pp[] below); this is its saturated value
     tc, dr = p0.solref
     if tc <= 0:
         raise UnsupportedModel("direct solref (negative) not supported")
@@ -238,6 +247,40 @@ def compile_model(spec: ModelSpec, env_kind: int, max_episode_steps: int, frame_
         c.chassis_half[:] = chassis_geoms[0].size
         c.chassis_pos[:] = chassis_geoms[0].pos
     c.frame_skip, c.max_episode_steps, c.env_kind = frame_skip, max_episode_steps, env_kind
+    c.nq, c.nv = spec.nq, spec.nv
+
+    def pair_params(p, tran_sum):
+        """{mu, K, B, D1, d0, d1, width, margin}: R_row = 2 mu^2 (1-imp)/imp tran (1+mu^2) (A.7) -> D = D1 imp/(1-imp)."""
+        a0, a1, width, mid, power = p.solimp
+        a0, a1 = (min(0.9999, max(0.0001, x)) for x in (a0, a1))
+        if (mid, power) != (0.5, 2.0) and a0 != a1:
+            raise UnsupportedModel("impedance curve other than midpoint 0.5 / power 2")
+        if p.condim != 3 or p.gap != 0 or p.friction[0] != p.friction[1] or p.solref[0] <= 0:
+            raise UnsupportedModel("pair outside the supported contact class")
+        tc_ = max(p.solref[0], 2 * spec.timestep)
+        Kp = 1.0 / max(MINVAL, a1 * a1 * tc_ * tc_ * p.solref[1] * p.solref[1])
+        Bp = 2.0 / max(MINVAL, a1 * tc_)
+        mu_ = p.friction[0]
+        return [mu_, Kp, Bp, 1.0 / (2 * mu_ * mu_ * tran_sum * (1 + mu_ * mu_)), a0, a1, max(width, 1e-15), p.margin]
+    c.pp[0][:] = pair_params(p0, tran)
+    if block is not None:
+        bb = spec.bodies[block]
+        bgeoms = [g for g in spec.geoms if g.body == block]
+        if len(bgeoms) != 1 or bgeoms[0].type != GEOM_BOX or len(set(bgeoms[0].size)) != 1 or tuple(bgeoms[0].pos) != (0, 0, 0) \
+                or np.linalg.norm(bb.ipos) > 1e-12:
+            raise UnsupportedModel("the block must be a single cube geom centred on its body")
+        Ib = np.asarray(bb.inertia)
+        if np.abs(Ib - Ib[0, 0] * np.eye(3)).max() > 1e-15:
+            raise UnsupportedModel("block inertia must be isotropic")
+        invw[bb.name] = (1.0 / bb.mass, 1.0 / Ib[0, 0])
+        gid = {id(g): k for k, g in enumerate(spec.geoms)}
+        fid, bid_, cid = gid[id(floor)], gid[id(bgeoms[0])], gid[id(chassis_geoms[0])]
+        by_geoms = {frozenset((p.geom1, p.geom2)): p for p in spec.pairs}
+        c.pp[1][:] = pair_params(by_geoms[frozenset((fid, bid_))], invw[bb.name][0])
+        c.pp[2][:] = pair_params(by_geoms[frozenset((cid, bid_))], invw[cb.name][0] + invw[bb.name][0])
+        hb = bgeoms[0].size[0]
+        c.blk_half, c.blk_mass, c.blk_inertia, c.blk_radius = hb, bb.mass, Ib[0, 0], hb * math.sqrt(3.0)
+        c.chassis_radius = float(np.linalg.norm(chassis_geoms[0].size))
     c.flags = 1 if actderiv_skip_clamped else 0
 
     # MuJoCo accumulates data.time += h once per substep in fp64; reproduce the exact sequence

@@ -20,11 +20,11 @@ REGISTRY = {
     "Env01-v1": EnvSpec("Env01-v1", 0, "scene_env01.xml", 6000, 6000, "balance_robot.envs.env01_v1:Env01"),
     "Env01-v2": EnvSpec("Env01-v2", 1, "scene_env01.xml", 6000, 6000, "balance_robot.envs.env01_v2:Env01_v2"),
     "Env01-v3": EnvSpec("Env01-v3", 2, "scene_env01.xml", 6000, 6000, "balance_robot.envs.env01_v3:Env01_v3"),
+    "Env03-v2": EnvSpec("Env03-v2", 3, "scene_env03.xml", 1200, 6000, "balance_robot.envs.env03_v2:Env03_v2"),
 }
 
 NOT_BUILT = {
-    "Env03-v2": "second free body + box contacts: SURVEY.md 8(f) row f2, not in the CUDA kernel yet",
-    "Env03-v1": "see Env03-v2",
+    "Env03-v1": "out of scope (the north star names Env03-v2; v1 fires the block from random directions)",
     "Env02-v1": "out of scope (not named in the north star)",
     "Env03-v1-fail": "out of scope (mesh drop scene)",
     "Cal01": "out of scope (open-loop calibration run)",

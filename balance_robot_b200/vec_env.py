@@ -138,7 +138,7 @@ class BalanceVecEnv:
         ru = None
         if replay_u is not None:
             ru = replay_u.to(self.device, torch.float64).contiguous()
-            assert ru.shape == (self.num_envs, 16)
+            assert ru.shape == (self.num_envs, 32 if self.spec.kind == 3 else 16)
         with torch.cuda.device(self.device):
             _cabi.check(L.brb_env_reset_all(self._env, self._obs.data_ptr(), ru.data_ptr() if ru is not None else None,
                                             self._stream()), "brb_env_reset_all")
@@ -177,7 +177,7 @@ class BalanceVecEnv:
         ru = None
         if replay_u is not None:
             ru = replay_u.to(self.device, torch.float64).contiguous()
-            assert ru.shape == (self.num_envs, 20)
+            assert ru.shape == (self.num_envs, 40 if self.spec.kind == 3 else 20)
         with torch.cuda.device(self.device):
             _cabi.check(L.brb_env_step(self._env, a.data_ptr(), self._obs.data_ptr(), self._rew.data_ptr(), self._done.data_ptr(),
                                        self._trunc.data_ptr(), self._tobs.data_ptr(), self._epr.data_ptr(), self._epl.data_ptr(),
@@ -221,10 +221,11 @@ class BalanceVecEnv:
 
     # ------------------------------------------------------------------ state access (trajectory checks)
     def get_state(self):
-        """(qpos [N,9], qvel [N,8], xquat [N,4]) fp64 CUDA tensors — MuJoCo's data.qpos / data.qvel / body xquat."""
+        """(qpos [N,nq], qvel [N,nv], xquat [N,4]) fp64 CUDA tensors — MuJoCo's data.qpos / data.qvel / chassis xquat
+        (nq, nv = 9, 8; Env03-v2 appends the block: 16, 14)."""
         n = self.num_envs
-        qpos = torch.empty((n, 9), dtype=torch.float64, device=self.device)
-        qvel = torch.empty((n, 8), dtype=torch.float64, device=self.device)
+        qpos = torch.empty((n, self.robot.consts.nq), dtype=torch.float64, device=self.device)
+        qvel = torch.empty((n, self.robot.consts.nv), dtype=torch.float64, device=self.device)
         xquat = torch.empty((n, 4), dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().brb_env_get_state(self._env, qpos.data_ptr(), qvel.data_ptr(), xquat.data_ptr(), self._stream()),
@@ -235,7 +236,7 @@ class BalanceVecEnv:
         """MujocoEnv.set_state (+ mj_forward): kinematics become fresh."""
         qpos = torch.as_tensor(qpos).to(self.device, torch.float64).contiguous()
         qvel = torch.as_tensor(qvel).to(self.device, torch.float64).contiguous()
-        assert qpos.shape == (self.num_envs, 9) and qvel.shape == (self.num_envs, 8)
+        assert qpos.shape == (self.num_envs, self.robot.consts.nq) and qvel.shape == (self.num_envs, self.robot.consts.nv)
         with torch.cuda.device(self.device):
             _cabi.check(_cabi.lib().brb_env_set_state(self._env, qpos.data_ptr(), qvel.data_ptr(), self._stream()), "brb_env_set_state")
 

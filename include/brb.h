@@ -9,7 +9,7 @@
  * fallback exists — without a CUDA device every compute entry point returns BRB_ECUDA.
  *
  * Layouts: obs [N,6] f32 row-major; actions [N,2] f32; reward [N] f32; done/truncated [N] u8;
- * terminal_obs [N,6] f32; ep_return [N] f32; ep_len [N] i32; qpos [N,9] f64; qvel [N,8] f64.
+ * terminal_obs [N,6] f32; ep_return [N] f32; ep_len [N] i32; qpos [N,nq] f64; qvel [N,nv] f64 (nq,nv = 9,8; Env03-v2: 16,14).
  */
 #ifndef BRB_H
 #define BRB_H
@@ -28,10 +28,11 @@ extern "C" {
 #define BRB_ENV01_V1 0 /* reference balance_robot/__init__.py:5-10  -> envs/env01_v1.py:10 */
 #define BRB_ENV01_V2 1 /* reference balance_robot/__init__.py:12-17 -> envs/env01_v2.py:14 */
 #define BRB_ENV01_V3 2 /* reference balance_robot/__init__.py:19-24 -> envs/env01_v3.py:13 */
+#define BRB_ENV03_V2 3 /* reference balance_robot/__init__.py:47-52 -> envs/env03_v2.py:14 (robot + fired block) */
 
 #define BRB_FLAG_ACTDERIV_SKIP_CLAMPED 1
 
-#define BRB_NSTATS 8
+#define BRB_NSTATS 12
 #define BRB_STAT_SUBSTEPS 0          /* env-substeps executed */
 #define BRB_STAT_CONTACT_SUBSTEPS 1  /* of which had >= 1 wheel-floor contact */
 #define BRB_STAT_SOLVES 2            /* 8x8 factorisations performed */
@@ -40,6 +41,8 @@ extern "C" {
 #define BRB_STAT_EPISODES 5          /* episodes finished */
 #define BRB_STAT_ENV_STEPS 6
 #define BRB_STAT_CONTACT_SLOTS 7     /* sum over contact substeps of the number of wheel-floor contacts (1..4) */
+#define BRB_STAT_COUPLED_SUBSTEPS 8  /* Env03-v2: substeps solved through the coupled 14-dof path (block touching the chassis) */
+#define BRB_STAT_BLOCK_CONTACT_SUBSTEPS 9 /* Env03-v2: substeps with the block on the floor */
 
 /* Per-model constant block, produced on the host by balance_robot_b200/model.py from the MJCF
  * (stands in for MjModel.from_xml_path, reference envs/RobotBaseEnv.py:56-65).  Passed to the
@@ -54,6 +57,11 @@ typedef struct BrbModelConsts {
   float impl_W[8], impl_G[3], impl_cinv_full, impl_cinv_damp;
   float chassis_half[3], chassis_pos[3];
   int frame_skip, max_episode_steps, env_kind, flags;
+  /* Env03-v2 only.  pp[k] = {mu, K, B, D1, d0, d1, width, margin} of the dynamic pairs k = 0 wheel-floor, 1 block-floor,
+   * 2 chassis-block (impedance imp(dist) from d0, d1, width; row D = D1 * imp / (1 - imp); aref = -B vel - K imp (dist - margin)) */
+  float pp[3][8];
+  float blk_half, blk_mass, blk_inertia, blk_radius, chassis_radius;
+  int nq, nv, reserved;
 } BrbModelConsts;
 
 typedef struct BrbModel BrbModel;
@@ -73,12 +81,13 @@ int brb_env_create(const BrbModel *m, int64_t n_envs, uint64_t seed, int64_t env
 void brb_env_destroy(BrbEnv *e);
 
 /* VecEnv.reset() -> MujocoEnv.reset -> reset_model (reference envs/env01_v1.py:39-58, env01_v2.py:52-71,
- * env01_v3.py:39-54).  replay_u_reset: optional [N,16] f64 uniforms replacing the Philox draws. */
+ * env01_v3.py:39-54, env03_v1.py:60-83).  replay_u_reset: optional [N,16] ([N,32] for Env03-v2) f64 uniforms replacing Philox. */
 int brb_env_reset_all(BrbEnv *e, float *obs, const double *replay_u_reset, void *stream);
 
 /* VecEnv.step(actions) (DummyVecEnv auto-reset + TimeLimit + Monitor around reference
  * envs/env01_v1.py:15-37 / env01_v2.py:28-50 / env01_v3.py:27-37, which call mujoco.mj_step x250).
- * replay_u: optional [N,20] f64 uniforms (4 step-noise slots then 16 reset slots) replacing Philox.
+ * replay_u: optional [N,20] f64 uniforms (4 step-noise slots then 16 reset slots) replacing Philox
+ * (Env03-v2: [N,40] = 8 re-fire slots then 32 reset slots).
  * terminal_obs rows are written only where done; ep_return / ep_len hold the running episode
  * statistics (the finished episode's totals where done). Any output pointer except obs may be NULL. */
 int brb_env_step(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,

@@ -12,12 +12,13 @@ EMU_DIR = ROOT / "tests" / "host_emu"
 EMU_LIB = EMU_DIR / "libbrb_emu.so"
 KERNEL_SRC = ROOT / "balance_robot_b200" / "csrc" / "brb_kernels.cu"
 
-ENV_IDS = {0: "Env01-v1", 1: "Env01-v2", 2: "Env01-v3"}
+ENV_IDS = {0: "Env01-v1", 1: "Env01-v2", 2: "Env01-v3", 3: "Env03-v2"}
 
 
 def build_emu() -> C.CDLL:
     deps = [EMU_DIR / "emu.cpp", EMU_DIR / "emu_shim.h", KERNEL_SRC, ROOT / "include" / "brb.h",
-            ROOT / "balance_robot_b200" / "csrc" / "brb_internal.h", ROOT / "balance_robot_b200" / "csrc" / "brb_chol8.inc"]
+            ROOT / "balance_robot_b200" / "csrc" / "brb_internal.h", ROOT / "balance_robot_b200" / "csrc" / "brb_chol8.inc", ROOT / "balance_robot_b200" / "csrc" / "brb_chol6.inc",
+            ROOT / "balance_robot_b200" / "csrc" / "brb_env03.cuh"]
     if not EMU_LIB.exists() or any(d.stat().st_mtime > EMU_LIB.stat().st_mtime for d in deps):
         subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-DBRB_HOST_EMU", "-I", str(EMU_DIR), "-mfma",
                         "-ffp-contract=fast", "-x", "c++", str(EMU_DIR / "emu.cpp"), "-o", str(EMU_LIB)], check=True)
@@ -41,6 +42,7 @@ class EmuVecEnv:
     def __init__(self, robot_model, n, seed=0, env0=0):
         self.E = build_emu()
         self.n = n
+        self.nq, self.nv = robot_model.consts.nq, robot_model.consts.nv
         tt = np.ascontiguousarray(robot_model.time_table)
         self.h = C.c_void_p(self.E.emu_create(C.addressof(robot_model.consts), tt.ctypes.data, len(tt), n, seed, env0))
         self.obs = np.zeros((n, 6), np.float32); self.rew = np.zeros(n, np.float32)
@@ -61,7 +63,7 @@ class EmuVecEnv:
         return self.obs.copy(), self.rew.copy(), self.done.copy(), self.trunc.copy()
 
     def get_state(self):
-        qp = np.zeros((self.n, 9)); qv = np.zeros((self.n, 8)); xq = np.zeros((self.n, 4))
+        qp = np.zeros((self.n, self.nq)); qv = np.zeros((self.n, self.nv)); xq = np.zeros((self.n, 4))
         self.E.emu_get_state(self.h, qp.ctypes.data, qv.ctypes.data, xq.ctypes.data)
         return qp, qv, xq
 
@@ -70,7 +72,7 @@ class EmuVecEnv:
         self.E.emu_set_state(self.h, qp.ctypes.data, qv.ctypes.data)
 
     def stats(self):
-        out = (C.c_ulonglong * 8)()
+        out = (C.c_ulonglong * 12)()
         self.E.emu_get_stats(self.h, out)
         return list(out)
 

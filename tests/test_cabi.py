@@ -34,8 +34,9 @@ def test_consts_struct_layout_matches_header():
     names = []
     for decl in re.findall(r"(?:float|int)\s+([^;]+);", body):
         for item in decl.split(","):
-            m = re.match(r"\s*(\w+)(?:\[(\d+)\])?", item)
-            names.append((m.group(1), int(m.group(2) or 1)))
+            m = re.match(r"\s*(\w+)((?:\[\d+\])*)", item)
+            dims = [int(x) for x in re.findall(r"\[(\d+)\]", m.group(2))]
+            names.append((m.group(1), int(np.prod(dims)) if dims else 1))
     fields = [(n, (C.sizeof(t) // 4)) for n, t in model.BrbModelConsts._fields_]
     assert names == fields
     assert C.sizeof(model.BrbModelConsts) == 4 * sum(k for _, k in names)

@@ -1,0 +1,79 @@
+"""-m gpu: Env03-v2 on the device through the C-ABI — same procedures as tests/test_env03_parity.py, plus device-vs-host
+equivalence of the same source and full-size properties."""
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from balance_robot_b200 import make_vec, mjcf, model
+from oracle import ref
+from test_env03_parity import env03_single_step
+from test_gpu_parity import GpuAdapter
+
+pytestmark = pytest.mark.gpu
+
+
+def test_reset_matches_oracle():
+    n, seed = 64, 3
+    env = GpuAdapter("Env03-v2", n, seed)
+    rv = ref.RefVecEnv(mjcf.parse("scene_env03.xml"), "Env03-v2", n, 1200, nthreads=8)
+    rv.set_attack_side(ref.env03_attack_side(seed, 0, n))
+    _, ur = ref.env03_draws(seed, 0, n, 0)
+    assert np.array_equal(rv.reset(ur), env.reset())
+    q, v = rv.get_state()
+    qd, vd, _ = env.get_state()
+    assert qd.shape == (n, 16) and vd.shape == (n, 14)
+    np.testing.assert_allclose(qd, q, atol=1e-14)
+    np.testing.assert_allclose(vd, v, atol=1e-13)
+    env.close(); rv.close()
+
+
+def test_single_step_parity_through_impacts():
+    n, seed = 32, 5
+    env = GpuAdapter("Env03-v2", n, seed)
+    rv = ref.RefVecEnv(mjcf.parse("scene_env03.xml"), "Env03-v2", n, 1200, nthreads=8)
+    rv.set_attack_side(ref.env03_attack_side(seed, 0, n))
+    er, eb, impacts = env03_single_step(env, rv, n, seed, 45)
+    assert impacts > 80
+    assert np.quantile(er, 0.99) < 1e-5 and (er >= 1e-5).mean() <= 0.02, (np.quantile(er, 0.99), er.max())
+    assert np.quantile(eb, 0.95) < 1e-5 and (eb >= 3e-5).mean() <= 0.03, (np.quantile(eb, 0.95), eb.max())
+    assert env.stats()["nonconverged"] == 0
+    env.close(); rv.close()
+
+
+def test_device_equals_host_emulation():
+    rm = model.compile_model(mjcf.parse("scene_env03.xml"), 3, 1200)
+    n = 16
+    gpu, emu = GpuAdapter("Env03-v2", n, 21), helpers.EmuVecEnv(rm, n, seed=21)
+    assert np.array_equal(gpu.reset(), emu.reset())
+    obs = gpu.reset()
+    emu.reset()
+    for t in range(12):
+        act = helpers.pd_policy(obs)
+        obs, rg, dg, _ = gpu.step(act)
+        oe, re_, de, _ = emu.step(act)
+        assert np.array_equal(dg, de)
+        qg, vg, _ = gpu.get_state()
+        qe, ve, _ = emu.get_state()
+        assert np.abs(qg - qe).max() < 2e-4 and np.abs(vg - ve).max() < 2e-2      # impacts amplify FMA-contraction differences
+    gpu.close(); emu.close()
+
+
+def test_full_size_properties_and_block_cycle():
+    n = 65536
+    env = make_vec("Env03-v2", n, seed=0)
+    obs = env.reset()
+    tot_done = 0
+    for t in range(160):
+        act = torch.as_tensor(helpers.pd_policy(obs.cpu().numpy())).cuda()
+        obs, r, d, info = env.step(act)
+        tot_done += int(d.sum())
+    qpos, qvel, xq = env.get_state()
+    assert torch.isfinite(qpos).all() and torch.isfinite(qvel).all() and torch.isfinite(obs).all()
+    assert (qpos[:, 3:7].norm(dim=1) - 1).abs().max() < 1e-6 and (qpos[:, 12:16].norm(dim=1) - 1).abs().max() < 1e-5
+    parked = ((qpos[:, 9] - 10).abs() < 0.5) & ((qpos[:, 10] - 10).abs() < 0.5)
+    assert 0.02 < parked.float().mean() < 0.98            # some blocks are parked waiting for their re-fire, some in play
+    st = env.stats()
+    assert st["episodes"] == tot_done and st["env_steps"] == 160 * n
+    assert st["nonconverged"] < 1e-4 * st["substeps"]
+    env.close()

@@ -87,16 +87,19 @@ def test_time_table_is_sequential_sum(spec):
 
 def test_unsupported_models_fail_loudly():
     with pytest.raises(model.UnsupportedModel):
-        model.compile_model(mjcf.parse("scene_env03.xml"), 0, 1200)
+        model.compile_model(mjcf.parse("scene_env03.xml"), 0, 1200)       # the block scene only compiles as Env03-v2
+    with pytest.raises(model.UnsupportedModel):
+        model.compile_model(mjcf.parse("scene_env01.xml"), 3, 1200)
     with pytest.raises(NotImplementedError):
-        registry.spec("Env03-v2")
+        registry.spec("Env03-v1")
     with pytest.raises(KeyError):
         registry.spec("Nope-v0")
 
 
 def test_registry_matches_reference_ids():
     assert registry.spec("Env01-v2").max_episode_steps == 6000
-    assert {k: v.kind for k, v in registry.REGISTRY.items()} == {"Env01-v1": 0, "Env01-v2": 1, "Env01-v3": 2}
+    assert {k: v.kind for k, v in registry.REGISTRY.items()} == {"Env01-v1": 0, "Env01-v2": 1, "Env01-v3": 2, "Env03-v2": 3}
+    assert registry.spec("Env03-v2").max_episode_steps == 1200
 
 
 @pytest.mark.skipif(not REF_ENVS.exists(), reason="reference tree only exists in the build container")
