@@ -16,13 +16,13 @@ CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "libbrb_cuda.so"
 _EXPERIMENT_LIB = "BRB_EXPERIMENT_LIB"   # kernel-tuning experiments only (scripts/): alternative build of the SAME sources
 SOURCES = ("brb_kernels.cu", "brb_cabi.cu")
-HEADERS = (CSRC / "brb_internal.h", CSRC / "brb_chol8.inc", CSRC / "brb_chol6.inc", CSRC / "brb_env03.cuh",
+HEADERS = (CSRC / "brb_internal.h", CSRC / "brb_chol8.inc", CSRC / "brb_chol6.inc", CSRC / "brb_schur6.inc", CSRC / "brb_env03.cuh",
            CSRC.parent.parent / "include" / "brb.h")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
 NSTATS = 12
-STAT_NAMES = ("substeps", "contact_substeps", "solves", "nonconverged", "unsupported", "episodes", "env_steps", "contact_slots", "coupled_substeps", "block_contact_substeps", "_", "_")
+STAT_NAMES = ("substeps", "contact_substeps", "solves", "nonconverged", "unsupported", "episodes", "env_steps", "contact_slots", "coupled_substeps", "block_contact_substeps", "coupled_fallbacks", "coupled_solves")
 
 EXPORTS = (
     "brb_version", "brb_strerror", "brb_model_create", "brb_model_destroy", "brb_env_create", "brb_env_destroy",

@@ -79,9 +79,8 @@ BRB_D unsigned blk_active_set(const BrbModelConsts &c, const Blk &B, const float
   return bits;
 }
 
-// block alone: (diag(m, I) + sum P' S P) a = f - sum P' S yhat, P = [1 | -[r]x], world coordinates
-BRB_D void blk_solve(const BrbModelConsts &c, const Blk &B, unsigned bits, float (&a)[6]) {
-  float H[21], r[6];
+// block: H = diag(m, I) + sum P' S P (packed lower 6x6), r = f - sum P' S yhat, P = [1 | -[r]x], world coordinates
+BRB_D void blk_assemble(const BrbModelConsts &c, const Blk &B, unsigned bits, float (&H)[21], float (&r)[6]) {
 #pragma unroll
   for (int k = 0; k < 21; k++) H[k] = 0.f;
   H[LT6(0, 0)] = c.blk_mass; H[LT6(1, 1)] = c.blk_mass; H[LT6(2, 2)] = c.blk_mass;
@@ -115,6 +114,12 @@ BRB_D void blk_solve(const BrbModelConsts &c, const Blk &B, unsigned bits, float
     r[4] += rz * gx - rx * gz;
     r[5] += -ry * gx + rx * gy;
   }
+}
+
+// block alone: one Newton step on its floor-contact active set
+BRB_D void blk_solve(const BrbModelConsts &c, const Blk &B, unsigned bits, float (&a)[6]) {
+  float H[21], r[6];
+  blk_assemble(c, B, bits, H, r);
 #include "brb_chol6.inc"
 #pragma unroll
   for (int k = 0; k < 6; k++) a[k] = r[k];
@@ -403,7 +408,7 @@ int env03_coupled_solve(const BrbModelConsts &c, const Phys &P, const GContact *
 }
 
 // ------------------------------------------------------------------------------------------------ substep driver
-struct Env03Stats { unsigned coupled, blk_contact, unsupported; };
+struct Env03Stats { unsigned coupled, blk_contact, unsupported, fallback, csolves; };
 
 // gathers every contact of the substep into generic records and runs the coupled solve
 BRB_D int env03_coupled_substep(const BrbModelConsts &c, const Phys &P, const Blk &B, const float (*bpos)[3], const float *bdist,
@@ -450,6 +455,151 @@ BRB_D int env03_coupled_substep(const BrbModelConsts &c, const Phys &P, const Bl
   return env03_coupled_solve(c, P, gc, n, acc);
 }
 
+// ------------------------------------------------------------------------------------------------ fast coupled path
+// Chassis-block contacts of the current substep (general contact frame).  Indexed at run time -> local memory; the
+// accumulators they feed (H, Hb, Cc) are indexed at compile time and stay in registers.
+struct CBSet {
+  float n[8][3], t1[8][3], t2[8][3], ra[8][3], rb[8][3], y[8][3], D[8];
+  int nc;
+  unsigned bits;   // 4 pyramid rows per contact
+};
+
+BRB_D void cb_setup(const BrbModelConsts &c, const Phys &P, const Blk &B, const float (*bpos)[3], const float *bdist, const float *bn,
+                    int nbb, CBSet &Q) {
+  const float *pp = c.pp[2];
+  const float wr[3] = {P.ex[0] * P.w[0].s + P.ey[0] * P.w[1].s + P.ez[0] * P.w[2].s, P.ex[1] * P.w[0].s + P.ey[1] * P.w[1].s + P.ez[1] * P.w[2].s,
+                       P.ex[2] * P.w[0].s + P.ey[2] * P.w[1].s + P.ez[2] * P.w[2].s};
+  const float wb[3] = {B.ex[0] * B.w[0] + B.ey[0] * B.w[1] + B.ez[0] * B.w[2], B.ex[1] * B.w[0] + B.ey[1] * B.w[1] + B.ez[1] * B.w[2],
+                       B.ex[2] * B.w[0] + B.ey[2] * B.w[1] + B.ez[2] * B.w[2]};
+  float nn[3] = {bn[0], bn[1], bn[2]}, t1[3], t2[3];
+  make_frame3(nn, t1, t2);
+  int n = 0;
+  for (int k2 = 0; k2 < nbb && n < 8; k2++) {
+    if (bdist[k2] >= pp[7]) continue;
+    float ra[3], rb[3];
+    for (int k = 0; k < 3; k++) { ra[k] = bpos[k2][k] - P.p[k].s; rb[k] = bpos[k2][k] - B.p[k]; }
+    const float dv[3] = {(B.v[0] + wb[1] * rb[2] - wb[2] * rb[1]) - (P.v[0].s + wr[1] * ra[2] - wr[2] * ra[1]),
+                         (B.v[1] + wb[2] * rb[0] - wb[0] * rb[2]) - (P.v[1].s + wr[2] * ra[0] - wr[0] * ra[2]),
+                         (B.v[2] + wb[0] * rb[1] - wb[1] * rb[0]) - (P.v[2].s + wr[0] * ra[1] - wr[1] * ra[0])};
+    const float imp = imp_of(pp, bdist[k2]);
+    Q.D[n] = pp[3] * imp / (1.f - imp);
+    for (int k = 0; k < 3; k++) { Q.n[n][k] = nn[k]; Q.t1[n][k] = t1[k]; Q.t2[n][k] = t2[k]; Q.ra[n][k] = ra[k]; Q.rb[n][k] = rb[k]; }
+    Q.y[n][0] = pp[2] * dot3f(nn, dv) + pp[1] * imp * (bdist[k2] - pp[7]);
+    Q.y[n][1] = pp[2] * dot3f(t1, dv);
+    Q.y[n][2] = pp[2] * dot3f(t2, dv);
+    n++;
+  }
+  Q.nc = n;
+}
+
+BRB_D unsigned cb_active_set(const BrbModelConsts &c, const CBSet &Q, const float (&ar)[8], const float (&ab)[6], unsigned prev) {
+  unsigned bits = 0;
+  const float mu = c.pp[2][0], eps = 2e-4f;
+  for (int k = 0; k < Q.nc; k++) {
+    const float *ra = Q.ra[k], *rb = Q.rb[k];
+    const float dx = (ab[0] + ab[4] * rb[2] - ab[5] * rb[1]) - (ar[0] + ar[4] * ra[2] - ar[5] * ra[1]);
+    const float dy = (ab[1] + ab[5] * rb[0] - ab[3] * rb[2]) - (ar[1] + ar[5] * ra[0] - ar[3] * ra[2]);
+    const float dz = (ab[2] + ab[3] * rb[1] - ab[4] * rb[0]) - (ar[2] + ar[3] * ra[1] - ar[4] * ra[0]);
+    const float z0 = Q.n[k][0] * dx + Q.n[k][1] * dy + Q.n[k][2] * dz + Q.y[k][0];
+    const float z1 = mu * (Q.t1[k][0] * dx + Q.t1[k][1] * dy + Q.t1[k][2] * dz + Q.y[k][1]);
+    const float z2 = mu * (Q.t2[k][0] * dx + Q.t2[k][1] * dy + Q.t2[k][2] * dz + Q.y[k][2]);
+    const unsigned pb = prev >> (4 * k);
+    const float e0 = (pb & 1u) ? eps : -eps, e1 = (pb & 2u) ? eps : -eps, e2 = (pb & 4u) ? eps : -eps, e3 = (pb & 8u) ? eps : -eps;
+    bits |= ((unsigned)(z0 + z1 < e0) | ((unsigned)(z0 - z1 < e1) << 1) | ((unsigned)(z0 + z2 < e2) << 2) | ((unsigned)(z0 - z2 < e3) << 3)) << (4 * k);
+  }
+  return bits;
+}
+
+// One Newton step of the coupled robot+block system on the given active sets: assemble the robot's 8x8 (H, r), the
+// block's 6x6 (Hb, rb) and the 6x6 coupling Cc from the chassis-block contacts, eliminate the block (brb_schur6.inc),
+// solve the reduced 8x8 (brb_chol8.inc), back-substitute the block.  Exact for fixed active sets (A.8).
+BRB_D void coupled_solve_fast(const BrbModelConsts &c, const Phys &P, const Blk &B, const CBSet &Q, float (&ar)[8], float (&ab)[6]) {
+  float H[36], r[8], Hb[21], rb[6], Cc[6][6];
+  phys_assemble<true>(c, P, P.valid ? P.bits : 0u, H, r);
+  blk_assemble(c, B, B.bits, Hb, rb);
+#pragma unroll
+  for (int i = 0; i < 6; i++)
+#pragma unroll
+    for (int j = 0; j < 6; j++) Cc[i][j] = 0.f;
+  const float mu = c.pp[2][0];
+  for (int k = 0; k < Q.nc; k++) {
+    const unsigned b = (Q.bits >> (4 * k)) & 15u;
+    if (!b) continue;
+    const float b0 = (float)(b & 1u), b1 = (float)((b >> 1) & 1u), b2 = (float)((b >> 2) & 1u), b3 = (float)((b >> 3) & 1u);
+    const float Dc = Q.D[k], Dm = Dc * mu, Dmm = Dm * mu;
+    const float W00 = Dc * (b0 + b1 + b2 + b3), W01 = Dm * (b0 - b1), W02 = Dm * (b2 - b3), W11 = Dmm * (b0 + b1), W22 = Dmm * (b2 + b3);
+    const float *n = Q.n[k], *t1 = Q.t1[k], *t2 = Q.t2[k];
+    float g0[3], g1[3], g2[3], S[3][3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) { g0[j] = W00 * n[j] + W01 * t1[j] + W02 * t2[j]; g1[j] = W01 * n[j] + W11 * t1[j]; g2[j] = W02 * n[j] + W22 * t2[j]; }
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) S[i][j] = n[i] * g0[j] + t1[i] * g1[j] + t2[i] * g2[j];
+    const float y0 = Q.y[k][0], y1 = Q.y[k][1], y2 = Q.y[k][2];
+    const float u0 = W00 * y0 + W01 * y1 + W02 * y2, u1 = W01 * y0 + W11 * y1, u2 = W02 * y0 + W22 * y2;
+    float gv[3];
+#pragma unroll
+    for (int j = 0; j < 3; j++) gv[j] = u0 * n[j] + u1 * t1[j] + u2 * t2[j];
+    const float ax = Q.ra[k][0], ay = Q.ra[k][1], az = Q.ra[k][2], bx = Q.rb[k][0], by = Q.rb[k][1], bz = Q.rb[k][2];
+    // T_j = S c_j with c_x = (0,-rz,ry), c_y = (rz,0,-rx), c_z = (-ry,rx,0), for the robot point (Ta) and the block point (Tb)
+    float Ta[3][3], Tb[3][3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      Ta[0][i] = -az * S[i][1] + ay * S[i][2]; Ta[1][i] = az * S[i][0] - ax * S[i][2]; Ta[2][i] = -ay * S[i][0] + ax * S[i][1];
+      Tb[0][i] = -bz * S[i][1] + by * S[i][2]; Tb[1][i] = bz * S[i][0] - bx * S[i][2]; Tb[2][i] = -by * S[i][0] + bx * S[i][1];
+    }
+    // c_i . v helpers
+#define CDOT_A(i, v) ((i) == 0 ? (-az * (v)[1] + ay * (v)[2]) : (i) == 1 ? (az * (v)[0] - ax * (v)[2]) : (-ay * (v)[0] + ax * (v)[1]))
+#define CDOT_B(i, v) ((i) == 0 ? (-bz * (v)[1] + by * (v)[2]) : (i) == 1 ? (bz * (v)[0] - bx * (v)[2]) : (-by * (v)[0] + bx * (v)[1]))
+    // robot block (J = -P_ra): + P_ra' S P_ra ; rhs + P_ra' gv
+    H[LT(0, 0)] += S[0][0]; H[LT(1, 0)] += S[1][0]; H[LT(2, 0)] += S[2][0]; H[LT(1, 1)] += S[1][1]; H[LT(2, 1)] += S[2][1]; H[LT(2, 2)] += S[2][2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) H[LT(3 + i, j)] += Ta[i][j];
+#pragma unroll
+      for (int j = 0; j <= i; j++) H[LT(3 + i, 3 + j)] += CDOT_A(i, Ta[j]);
+      r[i] += gv[i];
+      r[3 + i] += CDOT_A(i, gv);
+    }
+    // block (J = +P_rb): + P_rb' S P_rb ; rhs - P_rb' gv
+    Hb[LT6(0, 0)] += S[0][0]; Hb[LT6(1, 0)] += S[1][0]; Hb[LT6(2, 0)] += S[2][0]; Hb[LT6(1, 1)] += S[1][1]; Hb[LT6(2, 1)] += S[2][1]; Hb[LT6(2, 2)] += S[2][2];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+#pragma unroll
+      for (int j = 0; j < 3; j++) Hb[LT6(3 + i, j)] += Tb[i][j];
+#pragma unroll
+      for (int j = 0; j <= i; j++) Hb[LT6(3 + i, 3 + j)] += CDOT_B(i, Tb[j]);
+      rb[i] -= gv[i];
+      rb[3 + i] -= CDOT_B(i, gv);
+    }
+    // coupling: Cc[robot dof][block dof] = -(P_ra' S P_rb)
+#pragma unroll
+    for (int i = 0; i < 3; i++)
+#pragma unroll
+      for (int j = 0; j < 3; j++) {
+        Cc[i][j] -= S[i][j];
+        Cc[i][3 + j] -= Tb[j][i];
+        Cc[3 + i][j] -= Ta[i][j];
+        Cc[3 + i][3 + j] -= CDOT_A(i, Tb[j]);
+      }
+#undef CDOT_A
+#undef CDOT_B
+  }
+#define BRB_SCHUR6_ELIMINATE
+#include "brb_schur6.inc"
+#undef BRB_SCHUR6_ELIMINATE
+#include "brb_chol8.inc"
+#define BRB_SCHUR6_BACKSUB
+#include "brb_schur6.inc"
+#undef BRB_SCHUR6_BACKSUB
+#pragma unroll
+  for (int k = 0; k < 8; k++) ar[k] = r[k];
+#pragma unroll
+  for (int k = 0; k < 6; k++) ab[k] = rb[k];
+}
+
 // world-frame smooth force of the robot (phys_setup only fills it when a wheel touches the floor)
 BRB_D void phys_world_force(const BrbModelConsts &c, Phys &P) {
   const float n0 = P.ex[2], n1 = P.ey[2], n2 = P.ez[2];
@@ -476,73 +626,76 @@ BRB_D int env03_detect(const BrbModelConsts &c, const Phys &P, const Blk &B, flo
   return env03_box_box(pc, A, c.chassis_half, B.p, Bx, h2, c.pp[2][7], bpos, bdist, bn);
 }
 
+// nsub substeps as a per-lane state machine with ONE solve site: the robot (8 dofs), the block (6 dofs) and their coupling
+// always go through coupled_solve_fast (with no chassis-block contact the coupling block is zero and the elimination
+// decouples exactly).  A single code path keeps the loop body inside the instruction cache: the first version had
+// separate robot / block / coupled solvers and was fetch-bound (ncu: stall_no_instruction 4.9 per issue, profiles/).
 template <int MAXIT>
 BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&qstale)[4], float (&pstale)[3], Env03Stats &es) {
-  int sidx = 0, it = 0;
-  bool rconv = false, bconv = false;
-  float ra[8] = {0, 0, 0, 0, 0, 0, 0, 0}, ba[6] = {0, 0, 0, 0, 0, 0};
+  int sidx = 0, it = 0, nbb = 0, qprev_nc = -1;
+  bool need_setup = true;
   float bpos[8][3], bdist[8], bn[3];
-  phys_setup<true>(c, P);
-  blk_setup(c, B);
-  int nbb = env03_detect(c, P, B, bpos, bdist, bn);
+  CBSet Q;
+  Q.nc = 0; Q.bits = 0xFFFFFFFFu;
+  unsigned was = 0u;
+  int wasn = -1;
   for (;;) {
-    if (nbb > 0) {
-      float acc[14];
+    if (need_setup) {
+      phys_setup<true>(c, P);
       if (!P.valid) phys_world_force(c, P);
-      es.coupled++;
-      if (env03_coupled_substep(c, P, B, bpos, bdist, bn, nbb, acc)) P.n_nonconv++;
-      ra[0] = acc[0]; ra[1] = acc[1]; ra[2] = acc[2];
-      ra[3] = P.ex[0] * acc[3] + P.ex[1] * acc[4] + P.ex[2] * acc[5];
-      ra[4] = P.ey[0] * acc[3] + P.ey[1] * acc[4] + P.ey[2] * acc[5];
-      ra[5] = P.ez[0] * acc[3] + P.ez[1] * acc[4] + P.ez[2] * acc[5];
-      ra[6] = acc[6]; ra[7] = acc[7];
-#pragma unroll
-      for (int k = 0; k < 6; k++) ba[k] = acc[8 + k];
-      rconv = bconv = true;
-    } else {
-      if (!rconv) {
-        if (P.valid) {
-          float a[8];
-          phys_solve<true>(c, P, P.bits, a);
-          const unsigned nb = phys_active_set<true>(c, P, a, P.bits);
-          rconv = (nb == P.bits);
-          P.bits = nb;
-          if (!rconv && ++it >= MAXIT) { P.n_nonconv++; rconv = true; }
-          ra[0] = a[0]; ra[1] = a[1]; ra[2] = a[2];
-          ra[3] = P.ex[0] * a[3] + P.ex[1] * a[4] + P.ex[2] * a[5];
-          ra[4] = P.ey[0] * a[3] + P.ey[1] * a[4] + P.ey[2] * a[5];
-          ra[5] = P.ez[0] * a[3] + P.ez[1] * a[4] + P.ez[2] * a[5];
-          ra[6] = a[6]; ra[7] = a[7];
-        } else {
-          const float *f = P.fb;
-          const float u0 = c.minv_xy[0] * f[0] + c.minv_xy[1] * f[4];
-          const float u1 = c.minv_blk[0] * f[1] + c.minv_blk[1] * f[3] + c.minv_blk[2] * f[6] + c.minv_blk[3] * f[7];
-          const float u2 = c.minv_uz * f[2];
-          ra[0] = P.ex[0] * u0 + P.ey[0] * u1 + P.ez[0] * u2;
-          ra[1] = P.ex[1] * u0 + P.ey[1] * u1 + P.ez[1] * u2;
-          ra[2] = P.ex[2] * u0 + P.ey[2] * u1 + P.ez[2] * u2;
-          ra[3] = c.minv_blk[1] * f[1] + c.minv_blk[4] * f[3] + c.minv_blk[5] * f[6] + c.minv_blk[6] * f[7];
-          ra[4] = c.minv_xy[1] * f[0] + c.minv_xy[2] * f[4];
-          ra[5] = c.minv_wz * f[5];
-          ra[6] = c.minv_blk[2] * f[1] + c.minv_blk[5] * f[3] + c.minv_blk[7] * f[6] + c.minv_blk[8] * f[7];
-          ra[7] = c.minv_blk[3] * f[1] + c.minv_blk[6] * f[3] + c.minv_blk[8] * f[6] + c.minv_blk[9] * f[7];
-          rconv = true;
-        }
+      const unsigned fresh = P.valid & ~was;
+      P.bits |= ((fresh & 1u) ? 0xFu : 0u) | ((fresh & 2u) ? 0xF0u : 0u) | ((fresh & 4u) ? 0xF00u : 0u) | ((fresh & 8u) ? 0xF000u : 0u);
+      blk_setup(c, B);
+      if (B.nc != wasn) B.bits = 0xFFFFu;
+      nbb = env03_detect(c, P, B, bpos, bdist, bn);
+      Q.nc = 0;
+      if (nbb > 0) {
+        cb_setup(c, P, B, bpos, bdist, bn, nbb, Q);
+        if (Q.nc != qprev_nc) Q.bits = 0xFFFFFFFFu;
+        if (Q.nc > 0) es.coupled++;
       }
-      if (!bconv) {
-        if (B.nc > 0) {
-          blk_solve(c, B, B.bits, ba);
-          const unsigned nb = blk_active_set(c, B, ba, B.bits);
-          bconv = (nb == B.bits);
-          B.bits = nb;
-          if (!bconv && ++it >= 2 * MAXIT) { P.n_nonconv++; bconv = true; }
-        } else {
-          ba[0] = 0.f; ba[1] = 0.f; ba[2] = -c.grav; ba[3] = 0.f; ba[4] = 0.f; ba[5] = 0.f;
-          bconv = true;
-        }
-      }
+      qprev_nc = Q.nc;
+      was = P.valid; wasn = B.nc;
+      need_setup = false;
+      it = 0;
     }
-    if (rconv && bconv) {
+    float ar[8], ab[6];
+    bool conv = true;
+    if (P.valid || B.nc > 0 || Q.nc > 0) {
+      coupled_solve_fast(c, P, B, Q, ar, ab);
+      es.csolves++;
+      const unsigned nr = P.valid ? phys_active_set<true>(c, P, ar, P.bits) : P.bits;
+      const unsigned nbl = blk_active_set(c, B, ab, B.bits), nq = cb_active_set(c, Q, ar, ab, Q.bits);
+      conv = (nr == P.bits) && (nbl == B.bits) && (nq == Q.bits);
+      P.bits = nr; B.bits = nbl; Q.bits = nq;
+      if (!conv && ++it >= MAXIT) {
+        float acc[14];
+        es.fallback++;
+        if (env03_coupled_substep(c, P, B, bpos, bdist, bn, Q.nc > 0 ? nbb : 0, acc)) P.n_nonconv++;
+#pragma unroll
+        for (int k = 0; k < 8; k++) ar[k] = acc[k];
+#pragma unroll
+        for (int k = 0; k < 6; k++) ab[k] = acc[8 + k];
+        conv = true;
+      }
+    } else {
+      // both bodies in free flight: a_b(robot) = M_b^-1 f_b in the chassis frame, block = gravity
+      const float *f = P.fb;
+      const float u0 = c.minv_xy[0] * f[0] + c.minv_xy[1] * f[4];
+      const float u1 = c.minv_blk[0] * f[1] + c.minv_blk[1] * f[3] + c.minv_blk[2] * f[6] + c.minv_blk[3] * f[7];
+      const float u2 = c.minv_uz * f[2];
+      const float b0 = c.minv_blk[1] * f[1] + c.minv_blk[4] * f[3] + c.minv_blk[5] * f[6] + c.minv_blk[6] * f[7];
+      const float b1 = c.minv_xy[1] * f[0] + c.minv_xy[2] * f[4], b2 = c.minv_wz * f[5];
+#pragma unroll
+      for (int k = 0; k < 3; k++) {
+        ar[k] = P.ex[k] * u0 + P.ey[k] * u1 + P.ez[k] * u2;
+        ar[3 + k] = P.ex[k] * b0 + P.ey[k] * b1 + P.ez[k] * b2;          // world-frame angular acceleration
+      }
+      ar[6] = c.minv_blk[2] * f[1] + c.minv_blk[5] * f[3] + c.minv_blk[7] * f[6] + c.minv_blk[8] * f[7];
+      ar[7] = c.minv_blk[3] * f[1] + c.minv_blk[6] * f[3] + c.minv_blk[8] * f[6] + c.minv_blk[9] * f[7];
+      ab[0] = 0.f; ab[1] = 0.f; ab[2] = -c.grav; ab[3] = 0.f; ab[4] = 0.f; ab[5] = 0.f;
+    }
+    if (conv) {
       if (sidx == nsub - 1) {
 #pragma unroll
         for (int k = 0; k < 4; k++) qstale[k] = P.q[k];
@@ -550,19 +703,11 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
         for (int k = 0; k < 3; k++) pstale[k] = P.p[k].s - P.p[k].c;       // Q1: xpos is one substep stale too
       }
       if (B.nc > 0) es.blk_contact++;
-      phys_finalize(c, P, ra[0], ra[1], ra[2], ra[3], ra[4], ra[5], ra[6], ra[7]);
-      blk_finalize(c, B, ba);
+      phys_finalize(c, P, ar[0], ar[1], ar[2], P.ex[0] * ar[3] + P.ex[1] * ar[4] + P.ex[2] * ar[5],
+                    P.ey[0] * ar[3] + P.ey[1] * ar[4] + P.ey[2] * ar[5], P.ez[0] * ar[3] + P.ez[1] * ar[4] + P.ez[2] * ar[5], ar[6], ar[7]);
+      blk_finalize(c, B, ab);
       if (++sidx >= nsub) break;
-      const unsigned was = P.valid;
-      const int wasn = B.nc;
-      phys_setup<true>(c, P);
-      const unsigned fresh = P.valid & ~was;
-      P.bits |= ((fresh & 1u) ? 0xFu : 0u) | ((fresh & 2u) ? 0xF0u : 0u) | ((fresh & 4u) ? 0xF00u : 0u) | ((fresh & 8u) ? 0xF000u : 0u);
-      blk_setup(c, B);
-      if (B.nc != wasn) B.bits = 0xFFFFu;
-      nbb = env03_detect(c, P, B, bpos, bdist, bn);
-      rconv = bconv = false;
-      it = 0;
+      need_setup = true;
     }
   }
 }
@@ -638,7 +783,7 @@ BRB_D void reset_env03(const BrbState &S, long long i, const double *u, float o[
 BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long long i, const float *__restrict__ actions,
                       float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done,
                       uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs, float *__restrict__ ep_return_out,
-                      int32_t *__restrict__ ep_len_out, const double *__restrict__ replay_u, unsigned stat[10]) {
+                      int32_t *__restrict__ ep_len_out, const double *__restrict__ replay_u, unsigned stat[12]) {
   const long long N = S.n;
   double qvel[14], xq[4];
   for (int k = 0; k < 14; k++) qvel[k] = S.qvel[k * N + i];
@@ -676,10 +821,10 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
   }
   KF qprev[4];
   float pstale[3];
-  Env03Stats es = {0u, 0u, 0u};
+  Env03Stats es = {0u, 0u, 0u, 0u, 0u};
   phys03_run<BRB_MAXIT>(c, st, B, c.frame_skip, qprev, pstale, es);
   stat[0] = c.frame_skip; stat[1] = st.n_contact; stat[2] = st.n_solve; stat[3] = st.n_nonconv; stat[7] = st.n_slots;
-  stat[8] = es.coupled; stat[9] = es.blk_contact;
+  stat[8] = es.coupled; stat[9] = es.blk_contact; stat[10] = es.fallback; stat[11] = es.csolves;
   {
     const float drop = 0.005f * (fabsf(st.v[2].s) + 0.12f * (fabsf(st.w[0].s) + fabsf(st.w[1].s) + fabsf(st.w[2].s))) + 0.0005f;
     const bool far = phys_clearance(c, st) > drop;

@@ -6,6 +6,9 @@
 #ifndef BRB_BLOCK
 #define BRB_BLOCK 64    // threads per CTA of the step kernel (one env per thread)
 #endif
+#ifndef BRB_MINBLOCKS_ENV03
+#define BRB_MINBLOCKS_ENV03 4   // Env03-v2 carries the block and the coupled system: 255 registers, 4 CTAs per SM
+#endif
 #ifndef BRB_MINBLOCKS
 #define BRB_MINBLOCKS 6 // __launch_bounds__ min resident CTAs per SM (register cap = 65536 / (BRB_BLOCK * BRB_MINBLOCKS))
 #endif

@@ -395,10 +395,9 @@ BRB_D void contact_assemble(const BrbModelConsts &c, const Phys &P, unsigned bit
   }
 }
 
-// ---- one Newton step on the active set `bits`: (M' + sum P'SP) a = f - sum P'S yhat   (A.8; exact for a fixed set)
+// ---- H = M' + sum P'SP (packed lower 8x8), r = f - sum P'S yhat for the active set `bits`
 template <bool VI = false>
-BRB_D void phys_solve(const BrbModelConsts &c, Phys &P, unsigned bits, float (&a)[8]) {
-  float H[36], r[8];
+BRB_D void phys_assemble(const BrbModelConsts &c, const Phys &P, unsigned bits, float (&H)[36], float (&r)[8]) {
 #pragma unroll
   for (int k = 0; k < 36; k++) H[k] = 0.f;
   // M' = blockdiag(R, R, I) M_b blockdiag(R, R, I)'
@@ -427,6 +426,13 @@ BRB_D void phys_solve(const BrbModelConsts &c, Phys &P, unsigned bits, float (&a
   contact_assemble<1, VI>(c, P, bits, H, r);
   contact_assemble<2, VI>(c, P, bits, H, r);
   contact_assemble<3, VI>(c, P, bits, H, r);
+}
+
+// ---- one Newton step on the active set `bits`: (M' + sum P'SP) a = f - sum P'S yhat   (A.8; exact for a fixed set)
+template <bool VI = false>
+BRB_D void phys_solve(const BrbModelConsts &c, Phys &P, unsigned bits, float (&a)[8]) {
+  float H[36], r[8];
+  phys_assemble<VI>(c, P, bits, H, r);
   // Cholesky H = L L' and the two triangular solves, straight-line (generated: gen_chol8.py)
 #include "brb_chol8.inc"
 #pragma unroll
@@ -573,7 +579,7 @@ template <int KIND>
 BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long i, const float *__restrict__ actions,
                     float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done,
                     uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs, float *__restrict__ ep_return_out,
-                    int32_t *__restrict__ ep_len_out, const double *__restrict__ replay_u, unsigned stat[10]) {
+                    int32_t *__restrict__ ep_len_out, const double *__restrict__ replay_u, unsigned stat[12]) {
   const long long N = S.n;
   // ---------------- prologue (fp64 task logic on the pre-step state) ----------------
   double qvel[8], xq[4];
@@ -732,7 +738,7 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
 #define BRB_STEP_BOUNDS __launch_bounds__(BRB_BLOCK, BRB_MINBLOCKS)
 #endif
 template <int KIND>
-__global__ void BRB_STEP_BOUNDS brb_step_kernel(const __grid_constant__ BrbModelConsts c, const BrbState S, const BrbPerm perm,
+__global__ void __launch_bounds__(BRB_BLOCK, (KIND == BRB_ENV03_V2) ? BRB_MINBLOCKS_ENV03 : BRB_MINBLOCKS) brb_step_kernel(const __grid_constant__ BrbModelConsts c, const BrbState S, const BrbPerm perm,
                                                 const float *__restrict__ actions, float *__restrict__ obs,
                                                 float *__restrict__ reward, uint8_t *__restrict__ done,
                                                 uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs,
@@ -743,7 +749,7 @@ __global__ void BRB_STEP_BOUNDS brb_step_kernel(const __grid_constant__ BrbModel
   // envs are visited in the order of the partition built by the previous step: robots expected to stay airborne
   // first, grounded ones last, so a warp's lanes mostly run the same path (state columns are addressed by env id)
   const long long i = live ? (perm.in ? (long long)perm.in[tid] : tid) : 0;
-  unsigned stat[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  unsigned stat[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   if (live) {
     if (KIND == BRB_ENV03_V2) step_env03(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat);
     else step_env<KIND>(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat);
@@ -758,7 +764,7 @@ __global__ void BRB_STEP_BOUNDS brb_step_kernel(const __grid_constant__ BrbModel
   // statistics: one atomic per warp per counter
   const unsigned long long a0 = warp_sum(stat[0]), a1 = warp_sum(stat[1]), a2 = warp_sum(stat[2]), a3 = warp_sum(stat[3]),
                            a4 = warp_sum(stat[4]), a5 = warp_sum(stat[5]), a6 = warp_sum(live ? 1u : 0u), a7 = warp_sum(stat[7]),
-                           stat8 = warp_sum(stat[8]), stat9 = warp_sum(stat[9]);
+                           stat8 = warp_sum(stat[8]), stat9 = warp_sum(stat[9]), stat10 = warp_sum(stat[10]), stat11 = warp_sum(stat[11]);
   if ((threadIdx.x & 31) == 0) {
     atomicAdd(&S.stats[BRB_STAT_SUBSTEPS], a0);
     atomicAdd(&S.stats[BRB_STAT_CONTACT_SUBSTEPS], a1);
@@ -772,6 +778,8 @@ __global__ void BRB_STEP_BOUNDS brb_step_kernel(const __grid_constant__ BrbModel
       const unsigned long long a8 = stat8, a9 = stat9;
       if (a8) atomicAdd(&S.stats[BRB_STAT_COUPLED_SUBSTEPS], a8);
       if (a9) atomicAdd(&S.stats[BRB_STAT_BLOCK_CONTACT_SUBSTEPS], a9);
+      if (stat10) atomicAdd(&S.stats[10], (unsigned long long)stat10);
+      if (stat11) atomicAdd(&S.stats[11], (unsigned long long)stat11);
     }
   }
 }

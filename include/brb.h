@@ -43,6 +43,8 @@ extern "C" {
 #define BRB_STAT_CONTACT_SLOTS 7     /* sum over contact substeps of the number of wheel-floor contacts (1..4) */
 #define BRB_STAT_COUPLED_SUBSTEPS 8  /* Env03-v2: substeps solved through the coupled 14-dof path (block touching the chassis) */
 #define BRB_STAT_BLOCK_CONTACT_SUBSTEPS 9 /* Env03-v2: substeps with the block on the floor */
+#define BRB_STAT_COUPLED_FALLBACKS 10 /* Env03-v2: coupled substeps finished by the generic line-search solver */
+#define BRB_STAT_COUPLED_SOLVES 11    /* Env03-v2: fast coupled Newton steps */
 
 /* Per-model constant block, produced on the host by balance_robot_b200/model.py from the MJCF
  * (stands in for MjModel.from_xml_path, reference envs/RobotBaseEnv.py:56-65).  Passed to the

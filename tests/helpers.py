@@ -18,7 +18,7 @@ ENV_IDS = {0: "Env01-v1", 1: "Env01-v2", 2: "Env01-v3", 3: "Env03-v2"}
 def build_emu() -> C.CDLL:
     deps = [EMU_DIR / "emu.cpp", EMU_DIR / "emu_shim.h", KERNEL_SRC, ROOT / "include" / "brb.h",
             ROOT / "balance_robot_b200" / "csrc" / "brb_internal.h", ROOT / "balance_robot_b200" / "csrc" / "brb_chol8.inc", ROOT / "balance_robot_b200" / "csrc" / "brb_chol6.inc",
-            ROOT / "balance_robot_b200" / "csrc" / "brb_env03.cuh"]
+            ROOT / "balance_robot_b200" / "csrc" / "brb_env03.cuh", ROOT / "balance_robot_b200" / "csrc" / "brb_schur6.inc"]
     if not EMU_LIB.exists() or any(d.stat().st_mtime > EMU_LIB.stat().st_mtime for d in deps):
         subprocess.run(["g++", "-O2", "-fPIC", "-shared", "-std=c++17", "-DBRB_HOST_EMU", "-I", str(EMU_DIR), "-mfma",
                         "-ffp-contract=fast", "-x", "c++", str(EMU_DIR / "emu.cpp"), "-o", str(EMU_LIB)], check=True)

@@ -56,13 +56,15 @@ extern "C" void emu_reset(Emu *e, float *obs, const double *replay) {
 template <int KIND> static void step_all(Emu *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *trunc,
                                          float *tobs, float *epr, int32_t *epl, const double *replay) {
   for (long long i = 0; i < e->S.n; i++) {
-    unsigned stat[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned stat[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (KIND == BRB_ENV03_V2) step_env03(e->c, e->S, i, actions, obs, reward, done, trunc, tobs, epr, epl, replay, stat);
     else step_env<KIND>(e->c, e->S, i, actions, obs, reward, done, trunc, tobs, epr, epl, replay, stat);
     for (int k = 0; k < 6; k++) e->stats[k] += stat[k];
     e->stats[BRB_STAT_CONTACT_SLOTS] += stat[7];
     e->stats[BRB_STAT_COUPLED_SUBSTEPS] += stat[8];
     e->stats[BRB_STAT_BLOCK_CONTACT_SUBSTEPS] += stat[9];
+    e->stats[10] += stat[10];
+    e->stats[11] += stat[11];
     e->stats[BRB_STAT_ENV_STEPS] += 1;
   }
 }
