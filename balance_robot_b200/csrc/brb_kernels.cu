@@ -208,7 +208,7 @@ struct Phys {
   float fb[8];                              // the same in the chassis frame (free-flight path: a_b = M_b^-1 f_b)
   float cr[4][3], cw[4][3], cy[4][3];       // per contact: r_w (from the chassis origin), wheel column w_w, yhat (n, t1, t2)
   float cD[4];                              // per-contact row weight D (only with position-dependent impedance: Env03-v2)
-  unsigned valid;                           // bit ci: contact slot ci (2*wheel + rim end) is in contact
+  unsigned valid, valid_prev;               // bit ci: contact slot ci (2*wheel + rim end) is in contact (valid_prev: at step entry)
   bool clampL, clampR;                      // servo sits on its forcerange (A.9)
   unsigned n_contact, n_solve, n_nonconv, n_slots;
 };
@@ -489,8 +489,18 @@ BRB_D void phys_run(const BrbModelConsts &c, Phys &P, int nsub, KF (&qstale)[4])
   int sidx = 0, it = 0;
   // The active set of a new substep is seeded with the previous substep's converged set (rows of a contact that just
   // appeared start "all active"): right ~97 % of the time, and the post-solve check below catches the rest.
-  phys_setup(c, P);
+  // phys_setup has a single call site (flag instead of a second inlined copy) to keep the loop body small.
+  bool need_setup = true;
+  unsigned was = P.valid_prev;
   for (;;) {
+    if (need_setup) {
+      phys_setup(c, P);
+      const unsigned fresh = P.valid & ~was;     // slots that were not in contact a substep ago start with all four rows active
+      P.bits |= ((fresh & 1u) ? 0xFu : 0u) | ((fresh & 2u) ? 0xF0u : 0u) | ((fresh & 4u) ? 0xF00u : 0u) | ((fresh & 8u) ? 0xF000u : 0u);
+      was = P.valid;
+      need_setup = false;
+      it = 0;
+    }
     bool conv = true;
     float avx, avy, avz, ab0, ab1, ab2, a6, a7;
 #ifdef BRB_TRIPSTATS
@@ -537,12 +547,7 @@ BRB_D void phys_run(const BrbModelConsts &c, Phys &P, int nsub, KF (&qstale)[4])
       }
       phys_finalize(c, P, avx, avy, avz, ab0, ab1, ab2, a6, a7);
       if (++sidx >= nsub) break;
-      const unsigned was = P.valid;
-      phys_setup(c, P);
-      it = 0;
-      // slots that were not in contact a substep ago start with all four pyramid rows active
-      const unsigned fresh = P.valid & ~was;
-      P.bits |= ((fresh & 1u) ? 0xFu : 0u) | ((fresh & 2u) ? 0xF0u : 0u) | ((fresh & 4u) ? 0xF00u : 0u) | ((fresh & 8u) ? 0xF000u : 0u);
+      need_setup = true;
     }
   }
 }
@@ -634,6 +639,7 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
       st.ulo[k] = (float)(u - (double)st.uhi[k]);
     }
     st.bits = S.aset[i];
+    st.valid_prev = 0xFu;     // keep the persisted active set as it is on the first substep of the step
     st.n_contact = st.n_solve = st.n_nonconv = st.n_slots = 0;
   }
   const int nsub = c.frame_skip;
