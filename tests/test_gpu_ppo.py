@@ -37,12 +37,12 @@ def test_cli_train_writes_reference_style_artifacts(tmp_path):
     assert (run / "best_model.zip").exists()                                   # EvalCallback target, sb_rl.py:542
     assert list(run.glob("Env01-v2_PPO_cp__*_steps.zip"))                      # CheckpointCallback naming, sb_rl.py:545-550
     assert (tmp_path / "logs").is_dir() and (tmp_path / "movies").is_dir()
-    # fine-tune from the saved model with -m, as README.md:62 does for Env03-v2 (here: Env01-v3)
-    cmd2 = [sys.executable, str(ROOT / "sb_rl.py"), "-a", "PPO", "-m", str(run / "best_model.zip"), "train", "-e", "Env01-v3",
+    # fine-tune from the saved model with -m on Env03-v2, as README.md:62 does (BASELINE.json configs[3])
+    cmd2 = [sys.executable, str(ROOT / "sb_rl.py"), "-a", "PPO", "-m", str(run / "best_model.zip"), "train", "-e", "Env03-v2",
             "--num-envs", "512", "--total-timesteps", "20000", "--n-steps", "16"]
     res2 = subprocess.run(cmd2, cwd=tmp_path, capture_output=True, text=True, timeout=600)
     assert res2.returncode == 0, res2.stderr[-3000:]
-    assert (tmp_path / "models" / "Env01-v3_PPO").is_dir()
+    assert (tmp_path / "models" / "Env03-v2_PPO" / "Env03-v2_PPO_final.zip").exists()
 
 
 def test_policy_rollout_throughput_path_runs():
