@@ -307,7 +307,7 @@ int env03_coupled_solve(const BrbModelConsts &c, const Phys &P, const GContact *
     M[8][8] = M[9][9] = M[10][10] = c.blk_mass;
     M[11][11] = M[12][12] = M[13][13] = c.blk_inertia;
     for (int i = 0; i < 14; i++) for (int j = i + 1; j < 14; j++) M[i][j] = M[j][i];
-    for (int k = 0; k < 8; k++) f[k] = P.f[k];
+    { float fr[8]; phys_world_force(c, P, fr); for (int k = 0; k < 8; k++) f[k] = fr[k]; }
     f[8] = 0.f; f[9] = 0.f; f[10] = -c.blk_mass * c.grav; f[11] = f[12] = f[13] = 0.f;
   }
   // Newton with an exact line search on the piecewise-quadratic cost (the oracle's algorithm, A.8): start from the
@@ -600,18 +600,6 @@ BRB_D void coupled_solve_fast(const BrbModelConsts &c, const Phys &P, const Blk 
   for (int k = 0; k < 6; k++) ab[k] = rb[k];
 }
 
-// world-frame smooth force of the robot (phys_setup only fills it when a wheel touches the floor)
-BRB_D void phys_world_force(const BrbModelConsts &c, Phys &P) {
-  const float n0 = P.ex[2], n1 = P.ey[2], n2 = P.ez[2];
-#pragma unroll
-  for (int k = 0; k < 3; k++) {
-    P.f[k] = P.ex[k] * (P.fb[0] + mg_n(c, n0)) + P.ey[k] * (P.fb[1] + mg_n(c, n1)) + P.ez[k] * (P.fb[2] + mg_n(c, n2));
-    P.f[3 + k] = P.ex[k] * P.fb[3] + P.ey[k] * P.fb[4] + P.ez[k] * P.fb[5];
-  }
-  P.f[2] -= c.mass * c.grav;
-  P.f[6] = P.fb[6]; P.f[7] = P.fb[7];
-}
-
 // does the block touch the chassis box this substep?  bounding spheres first, then the SAT collider
 BRB_D int env03_detect(const BrbModelConsts &c, const Phys &P, const Blk &B, float (*bpos)[3], float *bdist, float *bn) {
   float pc[3];
@@ -642,7 +630,6 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
   for (;;) {
     if (need_setup) {
       phys_setup<true>(c, P);
-      if (!P.valid) phys_world_force(c, P);
       const unsigned fresh = P.valid & ~was;
       P.bits |= ((fresh & 1u) ? 0xFu : 0u) | ((fresh & 2u) ? 0xF0u : 0u) | ((fresh & 4u) ? 0xF00u : 0u) | ((fresh & 8u) ? 0xF000u : 0u);
       blk_setup(c, B);
@@ -680,7 +667,8 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
       }
     } else {
       // both bodies in free flight: a_b(robot) = M_b^-1 f_b in the chassis frame, block = gravity
-      const float *f = P.fb;
+      const float mg = c.mass * c.grav;
+      const float f[8] = {P.fb[0] - mg * P.ex[2], P.fb[1] - mg * P.ey[2], P.fb[2] - mg * P.ez[2], P.fb[3], P.fb[4], P.fb[5], P.fb[6], P.fb[7]};
       const float u0 = c.minv_xy[0] * f[0] + c.minv_xy[1] * f[4];
       const float u1 = c.minv_blk[0] * f[1] + c.minv_blk[1] * f[3] + c.minv_blk[2] * f[6] + c.minv_blk[3] * f[7];
       const float u2 = c.minv_uz * f[2];

@@ -191,7 +191,8 @@ BRB_D void reset_env(const BrbState &S, long long i, const double u[16], float o
 __device__ unsigned long long g_trip[8];   // debug: warp-trips, lane-trips, warp-trips with a solve, lanes solving
 #endif
 
-BRB_D float mg_n(const BrbModelConsts &c, float n) { return c.mass * c.grav * n; }
+// smooth force in the solver's coordinates: world linear (gravity = -m g e_z exactly), world angular, wheels
+BRB_D void phys_world_force(const BrbModelConsts &c, const struct Phys &P, float (&r)[8]);
 
 // Coordinates of the 8x8 contact system: world-frame linear acceleration (MuJoCo's own dofs 0-2), WORLD-frame angular
 // acceleration alpha_w = R alpha_b, wheel accelerations.  In these coordinates the contact frame of the z-up floor
@@ -204,14 +205,23 @@ struct Phys {
   unsigned bits;                            // converged pyramid-row active set of the last substep (4 bits per contact slot)
   // ---- working set of the current substep (phys_setup() .. phys_finalize())
   float ex[3], ey[3], ez[3];                // columns of R = chassis x/y/z axes in the world frame
-  float f[8];                               // smooth force: world linear (3), world angular (3), wheels (2)
-  float fb[8];                              // the same in the chassis frame (free-flight path: a_b = M_b^-1 f_b)
+  float fb[8];                              // smooth force in the chassis frame, WITHOUT gravity in the linear part (added per use)
   float cr[4][3], cw[4][3], cy[4][3];       // per contact: r_w (from the chassis origin), wheel column w_w, yhat (n, t1, t2)
   float cD[4];                              // per-contact row weight D (only with position-dependent impedance: Env03-v2)
   unsigned valid, valid_prev;               // bit ci: contact slot ci (2*wheel + rim end) is in contact (valid_prev: at step entry)
   bool clampL, clampR;                      // servo sits on its forcerange (A.9)
   unsigned n_contact, n_solve, n_nonconv, n_slots;
 };
+
+BRB_D void phys_world_force(const BrbModelConsts &c, const Phys &P, float (&r)[8]) {
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    r[k] = P.ex[k] * P.fb[0] + P.ey[k] * P.fb[1] + P.ez[k] * P.fb[2];
+    r[3 + k] = P.ex[k] * P.fb[3] + P.ey[k] * P.fb[4] + P.ez[k] * P.fb[5];
+  }
+  r[2] -= c.mass * c.grav;
+  r[6] = P.fb[6]; r[7] = P.fb[7];
+}
 
 // ---- A.3 steps 2-7: kinematics, smooth forces, collision, reference accelerations
 // impedance imp(dist) of a dynamic pair (solimp midpoint 0.5, power 2).  pp = {mu, K, B, D1, d0, d1, width, margin}
@@ -267,10 +277,10 @@ BRB_D void phys_setup(const BrbModelConsts &c, Phys &P) {
   const float n0 = P.ex[2], n1 = P.ey[2], n2 = P.ez[2];
   const float w0 = P.w[0].s, w1 = P.w[1].s, w2 = P.w[2].s, sL = P.s[0].s, sR = P.s[1].s;
   {
-    const float mg = c.mass * c.grav, gm = c.grav * c.mcz;
-    P.fb[0] = -c.mcz * (w0 * w2) - mg * n0;
-    P.fb[1] = -c.mcz * (w1 * w2) - mg * n1;
-    P.fb[2] = c.mcz * (w0 * w0 + w1 * w1) - mg * n2;
+    const float gm = c.grav * c.mcz;
+    P.fb[0] = -c.mcz * (w0 * w2);
+    P.fb[1] = -c.mcz * (w1 * w2);
+    P.fb[2] = c.mcz * (w0 * w0 + w1 * w1);
     const float Lx = c.Ixx * w0 + c.Ia * (sR - sL), Ly = c.Iyy * w1, Lz = c.Izz * w2;
     P.fb[3] = -(w1 * Lz - w2 * Ly) + gm * n1;
     P.fb[4] = -(w2 * Lx - w0 * Lz) - gm * n0;
@@ -297,14 +307,6 @@ BRB_D void phys_setup(const BrbModelConsts &c, Phys &P) {
   const float anx = fabsf(n0);
   const float dmin = common - c.ox * anx - c.hl * anx;          // lowest rim point of either wheel
   if (dmin < 0.f) {
-    // world-frame copies of what the contact rows need
-#pragma unroll
-    for (int k = 0; k < 3; k++) {
-      P.f[k] = P.ex[k] * (P.fb[0] + mg_n(c, n0)) + P.ey[k] * (P.fb[1] + mg_n(c, n1)) + P.ez[k] * (P.fb[2] + mg_n(c, n2));
-      P.f[3 + k] = P.ex[k] * P.fb[3] + P.ey[k] * P.fb[4] + P.ez[k] * P.fb[5];
-    }
-    P.f[2] -= c.mass * c.grav;                                   // R (-m g n_b) = -m g e_z exactly
-    P.f[6] = P.fb[6]; P.f[7] = P.fb[7];
     const float vy = -c.rad * n1 * irho, vz = -c.rad * n2 * irho;   // rim direction toward the floor, chassis frame: (0, vy, vz)
     const float sa = (n0 > 0.f) ? -1.f : 1.f;
     float G[3], A[3], B2[3], ww[3];
@@ -420,8 +422,7 @@ BRB_D void phys_assemble(const BrbModelConsts &c, const Phys &P, unsigned bits, 
     H[LT(7, 3)] = hx;  H[LT(7, 4)] = hy;  H[LT(7, 5)] = hz;
     H[LT(6, 6)] = c.Ia; H[LT(7, 7)] = c.Ia;
   }
-#pragma unroll
-  for (int k = 0; k < 8; k++) r[k] = P.f[k];
+  phys_world_force(c, P, r);
   contact_assemble<0, VI>(c, P, bits, H, r);
   contact_assemble<1, VI>(c, P, bits, H, r);
   contact_assemble<2, VI>(c, P, bits, H, r);
@@ -527,7 +528,8 @@ BRB_D void phys_run(const BrbModelConsts &c, Phys &P, int nsub, KF (&qstale)[4])
       a6 = a[6]; a7 = a[7];
     } else {
       // free flight: a_b = M_b^-1 f_b in the chassis frame, linear part rotated to the world
-      const float *f = P.fb;
+      const float mg = c.mass * c.grav;
+      const float f[8] = {P.fb[0] - mg * P.ex[2], P.fb[1] - mg * P.ey[2], P.fb[2] - mg * P.ez[2], P.fb[3], P.fb[4], P.fb[5], P.fb[6], P.fb[7]};
       const float u0 = c.minv_xy[0] * f[0] + c.minv_xy[1] * f[4];
       const float u1 = c.minv_blk[0] * f[1] + c.minv_blk[1] * f[3] + c.minv_blk[2] * f[6] + c.minv_blk[3] * f[7];
       const float u2 = c.minv_uz * f[2];
