@@ -35,8 +35,8 @@ ALG_FLOP_PER_ENV_STEP = FLOP_PER_SUBSTEP_CONTACT * FRAME_SKIP          # 9.25e5 
 ALG_BYTES_PER_ENV_STEP = 290.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum of brb_step_kernel<1> from the committed `ncu --set full` capture
-# (profiles/r1_step_kernel_ncu_raw.csv: 15,561,984 + 14,592 bytes for 65,536 robots) -> bytes per robot-step
-NCU_DRAM_BYTES_PER_ENV_STEP = (15561984 + 14592) / 65536
+# (profiles/r1_step_kernel_ncu_raw.csv: 13,964,288 + 5,632 bytes for 65,536 robots) -> bytes per robot-step
+NCU_DRAM_BYTES_PER_ENV_STEP = (13964288 + 5632) / 65536
 
 
 def parse_args():
@@ -274,7 +274,7 @@ def run_b200(args, rank, world, local_rank):
                 "frac": achieved / (fp32_peak / 1e12),
                 "traffic": NCU_DRAM_BYTES_PER_ENV_STEP * n,
                 "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r1_step_kernel_ncu_raw.csv "
-                                  "(237 B per robot-step, scaled to this shard); algorithmic bytes = 290 B per robot-step",
+                                  "(213 B per robot-step, scaled to this shard); algorithmic bytes = 290 B per robot-step",
                 "peak_source": "FFMA probe kernel measured in this run (brb_fp32_peak_flops); MEASURED_PEAKS.json has no FP32 entry; "
                                f"nominal {NOMINAL_FP32_TFLOPS:.1f}",
                 "algorithmic_flop_per_env_step": ALG_FLOP_PER_ENV_STEP,
