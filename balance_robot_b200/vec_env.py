@@ -53,6 +53,48 @@ ACTION_SPACE = Box([-1.0, -1.0], [1.0, 1.0])
 _NO_INFO: dict = {}
 
 
+class LazyInfoList(list):
+    """SB3's `infos`: a real list of dicts, one per env.  Envs that did not finish share one empty dict; the dicts of the
+    finished envs (terminal_observation / TimeLimit.truncated / Monitor's episode record) are built on first access, so a
+    step costs O(1) Python work instead of O(#done) when the consumer only looks at a few of them."""
+
+    def __init__(self, n, idx, tobs, trunc, epr, epl, t):
+        super().__init__([_NO_INFO] * n)
+        self._pending = {int(i): k for k, i in enumerate(idx)}
+        self._src = (tobs, trunc, epr, epl, t)
+
+    def _build(self, i):
+        k = self._pending.pop(i)
+        tobs, trunc, epr, epl, t = self._src
+        d = {"terminal_observation": tobs[k], "TimeLimit.truncated": bool(trunc[k]),
+             "episode": {"r": float(epr[k]), "l": int(epl[k]), "t": t}}
+        list.__setitem__(self, i, d)
+        return d
+
+    def __getitem__(self, i):
+        if isinstance(i, (int, np.integer)):
+            i = int(i)
+            if i < 0:
+                i += len(self)
+            if i in self._pending:
+                return self._build(i)
+        elif self._pending:
+            self._materialise()
+        return list.__getitem__(self, i)
+
+    def _materialise(self):
+        for i in list(self._pending):
+            self._build(i)
+
+    def __iter__(self):
+        self._materialise()
+        return list.__iter__(self)
+
+    def __eq__(self, other):
+        self._materialise()
+        return list.__eq__(self, other)
+
+
 class InfoBatch:
     """Tensor-valued infos of one step; `infos[i]` materialises the SB3 dict for env i."""
 
@@ -100,6 +142,7 @@ class BalanceVecEnv:
         _cabi.check(L.brb_model_create(C.byref(self.robot.consts), tt.ctypes.data, len(tt), dev_index, C.byref(self._model)),
                     "brb_model_create")
         self._env = C.c_void_p()
+        self._seed, self._env_id_offset, self._reseed = int(seed), int(env_id_offset), None
         _cabi.check(L.brb_env_create(self._model, self.num_envs, seed, env_id_offset, C.byref(self._env)), "brb_env_create")
         n, dv = self.num_envs, self.device
         self._obs = torch.zeros((n, 6), dtype=torch.float32, device=dv)
@@ -112,13 +155,11 @@ class BalanceVecEnv:
         if output == "numpy":
             pin = dict(pin_memory=True)
             self._h_act = torch.zeros((n, 2), dtype=torch.float32, **pin)
-            self._h_obs = torch.zeros((n, 6), dtype=torch.float32, **pin)
-            self._h_rew = torch.zeros(n, dtype=torch.float32, **pin)
-            self._h_done = torch.zeros(n, dtype=torch.uint8, **pin)
-            self._h_trunc = torch.zeros(n, dtype=torch.uint8, **pin)
-            self._h_tobs = torch.zeros((n, 6), dtype=torch.float32, **pin)
-            self._h_epr = torch.zeros(n, dtype=torch.float32, **pin)
-            self._h_epl = torch.zeros(n, dtype=torch.int32, **pin)
+            self._hbuf = [dict(obs=torch.zeros((n, 6), dtype=torch.float32, **pin), rew=torch.zeros(n, dtype=torch.float32, **pin),
+                               done=torch.zeros(n, dtype=torch.uint8, **pin), trunc=torch.zeros(n, dtype=torch.uint8, **pin),
+                               tobs=torch.zeros((n, 6), dtype=torch.float32, **pin), epr=torch.zeros(n, dtype=torch.float32, **pin),
+                               epl=torch.zeros(n, dtype=torch.int32, **pin)) for _ in range(2)]
+            self._flip = 0
         self._actions = None
         self._t0 = time.time()
         self.reset_infos: List[dict] = [{} for _ in range(min(n, 1))]
@@ -129,12 +170,23 @@ class BalanceVecEnv:
         return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
 
     def seed(self, seed: Optional[int] = None):
-        """SB3 VecEnv.seed: re-keys the Philox streams (takes effect at the next reset())."""
+        """SB3 VecEnv.seed: re-keys the Philox streams; takes effect at the next reset() (the env object is rebuilt)."""
         self._reseed = seed
-        return [seed] * min(self.num_envs, 1)
+        return [seed] * self.num_envs
+
+    def _apply_reseed(self) -> None:
+        seed, self._reseed = self._reseed, None
+        if seed is None:
+            return
+        L = _cabi.lib()
+        L.brb_env_destroy(self._env)
+        self._env = C.c_void_p()
+        self._seed = int(seed)
+        _cabi.check(L.brb_env_create(self._model, self.num_envs, self._seed, self._env_id_offset, C.byref(self._env)), "brb_env_create")
 
     def reset(self, replay_u: Optional[torch.Tensor] = None):
         L = _cabi.lib()
+        self._apply_reseed()
         ru = None
         if replay_u is not None:
             ru = replay_u.to(self.device, torch.float64).contiguous()
@@ -154,21 +206,18 @@ class BalanceVecEnv:
         if self.output == "numpy":
             a = np.asarray(self._actions, dtype=np.float32).reshape(self.num_envs, 2)
             self._h_act.numpy()[...] = a
-            _cabi.check(L.brb_env_step_host(self._env, self._h_act.data_ptr(), self._h_obs.data_ptr(), self._h_rew.data_ptr(),
-                                            self._h_done.data_ptr(), self._h_trunc.data_ptr(), self._h_tobs.data_ptr(),
-                                            self._h_epr.data_ptr(), self._h_epl.data_ptr()), "brb_env_step_host")
-            done = self._h_done.numpy().astype(bool)
-            # SB3 only reads infos: envs that did not finish share one empty dict, so this stays O(#done) per step
-            infos: List[dict] = [_NO_INFO] * self.num_envs
+            self._flip ^= 1
+            hb = self._hbuf[self._flip]
+            _cabi.check(L.brb_env_step_host(self._env, self._h_act.data_ptr(), hb["obs"].data_ptr(), hb["rew"].data_ptr(),
+                                            hb["done"].data_ptr(), hb["trunc"].data_ptr(), hb["tobs"].data_ptr(),
+                                            hb["epr"].data_ptr(), hb["epl"].data_ptr()), "brb_env_step_host")
+            done = hb["done"].numpy().astype(bool)
             idx = np.flatnonzero(done)
-            if idx.size:
-                tobs, trunc = self._h_tobs.numpy()[idx].copy(), self._h_trunc.numpy()[idx]
-                epr, epl = self._h_epr.numpy()[idx], self._h_epl.numpy()[idx]
-                t = round(time.time() - self._t0, 6)
-                for j, i in enumerate(idx.tolist()):
-                    infos[i] = {"terminal_observation": tobs[j], "TimeLimit.truncated": bool(trunc[j]),
-                                "episode": {"r": float(epr[j]), "l": int(epl[j]), "t": t}}
-            return self._h_obs.numpy().copy(), self._h_rew.numpy().copy(), done, infos
+            infos = LazyInfoList(self.num_envs, idx, hb["tobs"].numpy()[idx], hb["trunc"].numpy()[idx], hb["epr"].numpy()[idx],
+                                 hb["epl"].numpy()[idx], round(time.time() - self._t0, 6))
+            # the returned arrays are views of this step's pinned buffers; the other buffer set is used by the next step,
+            # so they stay valid for one more step() (SB3 copies them into its rollout buffer right away)
+            return hb["obs"].numpy(), hb["rew"].numpy(), done, infos
         a = self._actions
         if not isinstance(a, torch.Tensor):
             a = torch.as_tensor(np.asarray(a, dtype=np.float32))

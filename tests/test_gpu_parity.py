@@ -259,3 +259,15 @@ def test_episode_statistics_agree_with_oracle(spec):
     qo, qg = np.quantile(lo, [0.25, 0.5, 0.75]), np.quantile(lg, [0.25, 0.5, 0.75])
     assert np.all(np.abs(qo - qg) <= np.maximum(3, 0.25 * qg)), (qo, qg)
     env.close(); rv.close()
+
+
+def test_seed_rekeys_the_streams():
+    a = make_vec("Env01-v2", 64, seed=1)
+    o1 = a.reset().clone()
+    assert torch.equal(o1, a.reset())            # same seed, same reset draws (event 0)
+    a.seed(2)
+    o2 = a.reset().clone()
+    assert not torch.equal(o1, o2)
+    b = make_vec("Env01-v2", 64, seed=2)
+    assert torch.equal(o2, b.reset())
+    a.close(); b.close()
