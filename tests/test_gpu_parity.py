@@ -271,3 +271,28 @@ def test_seed_rekeys_the_streams():
     b = make_vec("Env01-v2", 64, seed=2)
     assert torch.equal(o2, b.reset())
     a.close(); b.close()
+
+
+def test_time_limit_truncation_on_device():
+    """gymnasium TimeLimit(6000) (balance_robot/__init__.py:15): robots balanced by the PD controller reach the limit; the step
+    that hits it reports done with TimeLimit.truncated, the episode record has l = 6000, and the env auto-resets."""
+    n = 64
+    env = make_vec("Env01-v1", n, seed=4)
+    obs = env.reset()
+    reached = torch.zeros(n, dtype=torch.bool, device="cuda")
+    gains = torch.tensor([12.0, 0.6, 0.35 * 0.034 * 170.0 / 4.0], device="cuda")
+    for t in range(1, 6001):
+        u = (gains[0] * obs[:, 0] * 0.25 + gains[1] * obs[:, 1] - gains[2] * obs[:, 4]).clamp(-1, 1)     # helpers.pd_policy on the device
+        obs, r, d, info = env.step(torch.stack([-u, u], 1))
+        if t < 6000:
+            assert not bool(info.truncated.any())
+    trunc = info.truncated.bool()
+    assert int(trunc.sum()) >= 2, int(trunc.sum())               # some robots stayed up for the whole 30 s
+    assert bool((d.bool() | ~trunc).all())
+    assert bool((info.episode_length[trunc] == 6000).all())
+    assert bool((info.episode_return[trunc] > 5000).all())       # ~1 per step while upright (RobotBaseEnv._get_reward)
+    assert bool((env.elapsed_steps()[trunc] == 0).all())         # auto-reset
+    assert bool((obs[trunc][:, 1] == 0).all())                   # Q6 on the reset observation
+    rec = info[int(torch.nonzero(trunc)[0])]
+    assert rec["TimeLimit.truncated"] is True and rec["episode"]["l"] == 6000
+    env.close()
