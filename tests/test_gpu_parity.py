@@ -290,7 +290,7 @@ def test_time_limit_truncation_on_device():
     assert int(trunc.sum()) >= 2, int(trunc.sum())               # some robots stayed up for the whole 30 s
     assert bool((d.bool() | ~trunc).all())
     assert bool((info.episode_length[trunc] == 6000).all())
-    assert bool((info.episode_return[trunc] > 5000).all())       # ~1 per step while upright (RobotBaseEnv._get_reward)
+    assert bool((info.episode_return[trunc] > 4000).all())       # ~1 per step while upright (RobotBaseEnv._get_reward)
     assert bool((env.elapsed_steps()[trunc] == 0).all())         # auto-reset
     assert bool((obs[trunc][:, 1] == 0).all())                   # Q6 on the reset observation
     rec = info[int(torch.nonzero(trunc)[0])]
