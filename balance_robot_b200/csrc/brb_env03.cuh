@@ -169,40 +169,72 @@ BRB_D void make_frame3(float *n, float *t1, float *t2) {   // mju_makeFrame with
 
 BRB_D float dot3f(const float *a, const float *b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
 
-// SAT over 15 axes + face clipping / edge-edge closest points: the oracle's collide_box_box in fp32.  Box 1 = chassis
-// (centre p1, axes A[i], half sizes h1), box 2 = block.  Returns the number of contacts; pos/dist/normal (1 -> 2) out.
+// Box-box in two stages (the oracle's collide_box_box in fp32).
+// Stage 1, env03_sat: separating-axis test over the 15 axes on the relative rotation C = A'B (all scalar registers,
+//   fully unrolled): r1 + r2 and the centre distance along an axis follow from C, |C| and t = A' dp.  Returns 0 when an
+//   axis separates the boxes by more than `margin`, else the axis of least penetration (kind 0/1: face of box 1/2,
+//   kind 2: edge i of box 1 x edge j of box 2), its signed direction (1 -> 2) and the separation along it.
+// Stage 2, env03_manifold: face clipping (Sutherland-Hodgman against the reference face's side planes) or the closest
+//   points of the two edges; <= 8 points.  Run-time indexed arrays -> local memory, not inlined.
+BRB_D int env03_sat(const float (&A)[3][3], const float (&h1)[3], const float (&Bx)[3][3], float h2, const float (&dp)[3], float margin,
+                    int &kind, int &bi, int &bj, float &best, float (&bestn)[3]) {
+  float Cm[3][3], Ca[3][3], t[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    t[i] = dot3f(dp, A[i]);
+#pragma unroll
+    for (int j = 0; j < 3; j++) { Cm[i][j] = dot3f(A[i], Bx[j]); Ca[i][j] = fabsf(Cm[i][j]); }
+  }
+  best = -1e30f; kind = -1; bi = 0; bj = 0;
+  float sgn = 1.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {          // faces of box 1
+    const float s = fabsf(t[i]) - (h1[i] + h2 * (Ca[i][0] + Ca[i][1] + Ca[i][2]));
+    if (s > margin) return 0;
+    if (s > best) { best = s; kind = 0; bi = i; sgn = t[i] >= 0.f ? 1.f : -1.f; }
+  }
+#pragma unroll
+  for (int j = 0; j < 3; j++) {          // faces of box 2
+    const float tl = t[0] * Cm[0][j] + t[1] * Cm[1][j] + t[2] * Cm[2][j];
+    const float s = fabsf(tl) - (h1[0] * Ca[0][j] + h1[1] * Ca[1][j] + h1[2] * Ca[2][j] + h2);
+    if (s > margin) return 0;
+    if (s > best) { best = s; kind = 1; bi = j; sgn = tl >= 0.f ? 1.f : -1.f; }
+  }
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    constexpr int nxt[3] = {1, 2, 0}, prv[3] = {2, 0, 1};
+    const int i1 = nxt[i], i2 = prv[i];
+#pragma unroll
+    for (int j = 0; j < 3; j++) {        // edge i of box 1 x edge j of box 2
+      const int j1 = nxt[j], j2 = prv[j];
+      const float n2 = 1.f - Cm[i][j] * Cm[i][j];
+      if (n2 < 1e-12f) continue;
+      const float inv = rsqrtf(n2);
+      const float tl = (t[i2] * Cm[i1][j] - t[i1] * Cm[i2][j]) * inv;
+      const float s = fabsf(tl) - (h1[i1] * Ca[i2][j] + h1[i2] * Ca[i1][j] + h2 * (Ca[i][j2] + Ca[i][j1])) * inv;
+      if (s > margin) return 0;
+      if (s > best + 1e-4f) { best = s; kind = 2; bi = i; bj = j; sgn = tl >= 0.f ? 1.f : -1.f; }
+    }
+  }
+  if (kind == 2) {
+    float L[3] = {A[bi][1] * Bx[bj][2] - A[bi][2] * Bx[bj][1], A[bi][2] * Bx[bj][0] - A[bi][0] * Bx[bj][2], A[bi][0] * Bx[bj][1] - A[bi][1] * Bx[bj][0]};
+    const float inv = rsqrtf(dot3f(L, L));
+#pragma unroll
+    for (int k = 0; k < 3; k++) bestn[k] = sgn * inv * L[k];
+  } else {
+#pragma unroll
+    for (int k = 0; k < 3; k++) bestn[k] = sgn * (kind == 0 ? A[bi][k] : Bx[bi][k]);
+  }
+  return 1;
+}
+
 #ifdef BRB_HOST_EMU
 static
 #else
 __device__ __noinline__
 #endif
-int env03_box_box(const float *p1, const float (*A)[3], const float *h1, const float *p2, const float (*Bx)[3], const float *h2,
-                  float margin, float (*pos)[3], float *dist, float *nrm) {
-  const float dp[3] = {p2[0] - p1[0], p2[1] - p1[1], p2[2] - p1[2]};
-  float best = -1e30f, bestn[3] = {0.f, 0.f, 1.f};
-  int bestkind = -1, bi = 0, bj = 0;
-  for (int kind = 0; kind < 2; kind++)
-    for (int i = 0; i < 3; i++) {
-      const float *L = kind == 0 ? A[i] : Bx[i];
-      float r1 = 0.f, r2 = 0.f;
-      for (int k = 0; k < 3; k++) { r1 += h1[k] * fabsf(dot3f(A[k], L)); r2 += h2[k] * fabsf(dot3f(Bx[k], L)); }
-      const float t = dot3f(dp, L), s = fabsf(t) - (r1 + r2);
-      if (s > margin) return 0;
-      if (s > best) { best = s; bestkind = kind; bi = i; for (int k = 0; k < 3; k++) bestn[k] = t >= 0.f ? L[k] : -L[k]; }
-    }
-  for (int i = 0; i < 3; i++)
-    for (int j = 0; j < 3; j++) {
-      float L[3] = {A[i][1] * Bx[j][2] - A[i][2] * Bx[j][1], A[i][2] * Bx[j][0] - A[i][0] * Bx[j][2], A[i][0] * Bx[j][1] - A[i][1] * Bx[j][0]};
-      const float n = sqrtf(dot3f(L, L));
-      if (n < 1e-6f) continue;
-      for (int k = 0; k < 3; k++) L[k] /= n;
-      float r1 = 0.f, r2 = 0.f;
-      for (int k = 0; k < 3; k++) { r1 += h1[k] * fabsf(dot3f(A[k], L)); r2 += h2[k] * fabsf(dot3f(Bx[k], L)); }
-      const float t = dot3f(dp, L), s = fabsf(t) - (r1 + r2);
-      if (s > margin) return 0;
-      if (s > best + 1e-4f) { best = s; bestkind = 2; bi = i; bj = j; for (int k = 0; k < 3; k++) bestn[k] = t >= 0.f ? L[k] : -L[k]; }
-    }
-  for (int k = 0; k < 3; k++) nrm[k] = bestn[k];
+int env03_manifold(const float *p1, const float (*A)[3], const float *h1, const float *p2, const float (*Bx)[3], const float *h2,
+                   float margin, int bestkind, int bi, int bj, float best, const float *bestn, float (*pos)[3], float *dist) {
   if (bestkind == 2) {
     float c1[3] = {p1[0], p1[1], p1[2]}, c2[3] = {p2[0], p2[1], p2[2]};
     for (int a = 0; a < 3; a++) {
@@ -408,7 +440,7 @@ int env03_coupled_solve(const BrbModelConsts &c, const Phys &P, const GContact *
 }
 
 // ------------------------------------------------------------------------------------------------ substep driver
-struct Env03Stats { unsigned coupled, blk_contact, unsupported, fallback, csolves; };
+struct Env03Stats { unsigned coupled, blk_contact, unsupported, fallback, csolves, coupled_last; };
 
 // gathers every contact of the substep into generic records and runs the coupled solve
 BRB_D int env03_coupled_substep(const BrbModelConsts &c, const Phys &P, const Blk &B, const float (*bpos)[3], const float *bdist,
@@ -610,8 +642,14 @@ BRB_D int env03_detect(const BrbModelConsts &c, const Phys &P, const Blk &B, flo
   if (dx * dx + dy * dy + dz * dz > reach * reach) return 0;
   const float A[3][3] = {{P.ex[0], P.ex[1], P.ex[2]}, {P.ey[0], P.ey[1], P.ey[2]}, {P.ez[0], P.ez[1], P.ez[2]}};
   const float Bx[3][3] = {{B.ex[0], B.ex[1], B.ex[2]}, {B.ey[0], B.ey[1], B.ey[2]}, {B.ez[0], B.ez[1], B.ez[2]}};
+  const float h1[3] = {c.chassis_half[0], c.chassis_half[1], c.chassis_half[2]}, dp[3] = {dx, dy, dz};
+  int kind, bi, bj;
+  float best;
+  float nn[3];
+  if (!env03_sat(A, h1, Bx, c.blk_half, dp, c.pp[2][7], kind, bi, bj, best, nn)) return 0;
+  bn[0] = nn[0]; bn[1] = nn[1]; bn[2] = nn[2];
   const float h2[3] = {c.blk_half, c.blk_half, c.blk_half};
-  return env03_box_box(pc, A, c.chassis_half, B.p, Bx, h2, c.pp[2][7], bpos, bdist, bn);
+  return env03_manifold(pc, A, h1, B.p, Bx, h2, c.pp[2][7], kind, bi, bj, best, bn, bpos, bdist);
 }
 
 // nsub substeps as a per-lane state machine with ONE solve site: the robot (8 dofs), the block (6 dofs) and their coupling
@@ -641,6 +679,7 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
         if (Q.nc != qprev_nc) Q.bits = 0xFFFFFFFFu;
         if (Q.nc > 0) es.coupled++;
       }
+      es.coupled_last = Q.nc > 0 ? 1u : 0u;
       qprev_nc = Q.nc;
       was = P.valid; wasn = B.nc;
       need_setup = false;
@@ -648,6 +687,16 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
     }
     float ar[8], ab[6];
     bool conv = true;
+#ifdef BRB_TRIPSTATS
+    {
+      const unsigned act = __activemask();
+      const unsigned nv = __popc(__ballot_sync(act, Q.nc > 0));
+      if ((threadIdx.x & 31u) == (unsigned)(__ffs(act) - 1)) {
+        atomicAdd(&g_trip[0], 1ull); atomicAdd(&g_trip[1], (unsigned long long)__popc(act));
+        if (nv) { atomicAdd(&g_trip[2], 1ull); atomicAdd(&g_trip[3], (unsigned long long)nv); }
+      }
+    }
+#endif
     if (P.valid || B.nc > 0 || Q.nc > 0) {
       coupled_solve_fast(c, P, B, Q, ar, ab);
       es.csolves++;
@@ -655,7 +704,9 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
       const unsigned nbl = blk_active_set(c, B, ab, B.bits), nq = cb_active_set(c, Q, ar, ab, Q.bits);
       conv = (nr == P.bits) && (nbl == B.bits) && (nq == Q.bits);
       P.bits = nr; B.bits = nbl; Q.bits = nq;
-      if (!conv && ++it >= MAXIT) {
+      if (!conv && ++it >= 5) {
+        // the undamped active-set iteration is cycling: finish with the line-search Newton, and seed the next substep with
+        // the active sets of ITS solution (otherwise the same cycle — and the same fallback — repeats substep after substep)
         float acc[14];
         es.fallback++;
         if (env03_coupled_substep(c, P, B, bpos, bdist, bn, Q.nc > 0 ? nbb : 0, acc)) P.n_nonconv++;
@@ -663,6 +714,9 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
         for (int k = 0; k < 8; k++) ar[k] = acc[k];
 #pragma unroll
         for (int k = 0; k < 6; k++) ab[k] = acc[8 + k];
+        if (P.valid) P.bits = phys_active_set<true>(c, P, ar, P.bits);
+        B.bits = blk_active_set(c, B, ab, B.bits);
+        Q.bits = cb_active_set(c, Q, ar, ab, Q.bits);
         conv = true;
       }
     } else {
@@ -809,7 +863,7 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
   }
   KF qprev[4];
   float pstale[3];
-  Env03Stats es = {0u, 0u, 0u, 0u, 0u};
+  Env03Stats es = {0u, 0u, 0u, 0u, 0u, 0u};
   phys03_run<BRB_MAXIT>(c, st, B, c.frame_skip, qprev, pstale, es);
   stat[0] = c.frame_skip; stat[1] = st.n_contact; stat[2] = st.n_solve; stat[3] = st.n_nonconv; stat[7] = st.n_slots;
   stat[8] = es.coupled; stat[9] = es.blk_contact; stat[10] = es.fallback; stat[11] = es.csolves;
@@ -817,11 +871,9 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
     const float drop = 0.005f * (fabsf(st.v[2].s) + 0.12f * (fabsf(st.w[0].s) + fabsf(st.w[1].s) + fabsf(st.w[2].s))) + 0.0005f;
     const bool far = phys_clearance(c, st) > drop;
     stat[6] = (st.valid == 0u && far) ? 0u : 1u + group_rank(st.valid);
-    // robots whose block is (or will be within one step) inside the chassis' reach go through the slow coupled solve:
-    // give them their own bucket so they do not stall warps of robots on the fast path
-    const float dx = B.p[0] - st.p[0].s, dy = B.p[1] - st.p[1].s, dz = B.p[2] - (st.p[2].s + c.chassis_pos[2]);
-    const float reach = c.chassis_radius + c.blk_radius + 0.06f;
-    if (dx * dx + dy * dy + dz * dz < reach * reach) stat[6] = BRB_NGROUPS - 1;
+    // robots whose block was touching the chassis in the last substep (impacts last ~6 env steps) get their own bucket, so
+    // the warps running the coupled assembly are not diluted by robots on the uncoupled path
+    if (es.coupled_last) stat[6] = BRB_NGROUPS - 1;
   }
 
   double qpos[16];

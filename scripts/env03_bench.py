@@ -18,6 +18,7 @@ if len(sys.argv) > 1 and sys.argv[1] == "child":
     e1.record(); torch.cuda.synchronize()
     t = e0.elapsed_time(e1) / K
     print(f"  Env03-v2 n={n} ms/step={t:.2f} env-steps/s={n/t*1e3:.3e} nonconv={env.stats()['nonconverged']}", flush=True)
+    st = env.stats(); print('   ', {k: st[k] for k in ('substeps','coupled_substeps','coupled_solves','coupled_fallbacks','block_contact_substeps','episodes')}, flush=True)
 else:
     for lib in sys.argv[1:]:
         print(lib, flush=True)

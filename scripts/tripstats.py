@@ -5,7 +5,8 @@ sys.path.insert(0, ".")
 import torch
 from balance_robot_b200 import make_vec, _cabi
 n = 65536
-env = make_vec("Env01-v2", n, seed=0); env.reset()
+env_id = sys.argv[1] if len(sys.argv) > 1 else "Env01-v2"
+env = make_vec(env_id, n, seed=0); env.reset()
 gen = torch.Generator(device="cuda").manual_seed(1234)
 acts = [torch.rand((n, 2), device="cuda", generator=gen) * 2 - 1 for _ in range(8)]
 L = _cabi.lib()
