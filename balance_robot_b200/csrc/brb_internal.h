@@ -4,13 +4,13 @@
 #include <stdint.h>
 
 #ifndef BRB_BLOCK
-#define BRB_BLOCK 64    // threads per CTA of the step kernel (one env per thread)
+#define BRB_BLOCK 128   // threads per CTA of the step kernel (one env per thread): one warp per SM sub-partition
 #endif
 #ifndef BRB_MINBLOCKS_ENV03
-#define BRB_MINBLOCKS_ENV03 4   // Env03-v2 carries the block and the coupled system: 255 registers, 4 CTAs per SM
+#define BRB_MINBLOCKS_ENV03 2   // Env03-v2 carries the block and the coupled system: 255 registers, 2 CTAs per SM
 #endif
 #ifndef BRB_MINBLOCKS
-#define BRB_MINBLOCKS 6 // __launch_bounds__ min resident CTAs per SM (register cap = 65536 / (BRB_BLOCK * BRB_MINBLOCKS))
+#define BRB_MINBLOCKS 3 // __launch_bounds__ min resident CTAs per SM (register cap = 65536 / (BRB_BLOCK * BRB_MINBLOCKS))
 #endif
 #define BRB_MAXIT 8     // cap on active-set (Newton) iterations per substep
 
@@ -37,9 +37,10 @@ struct BrbState {
 };
 
 // Visit order of the step kernel: `in` = order for this launch (NULL = identity).  The launch publishes a group key per
-// env (0 = far airborne, 1.. = by wheel-rim contact pattern) plus a histogram; brb_group_kernel counting-sorts them into the
+// env (0 = far airborne, then by landing time, then by wheel-rim contact pattern) plus a histogram; brb_group_kernel counting-sorts them into the
 // next launch's order, so that the lanes of a warp mostly run the same contact path.
-#define BRB_NGROUPS 18
+#define BRB_NLAND 8        // landing-time bins of airborne robots that will touch down during the next step
+#define BRB_NGROUPS (1 + BRB_NLAND + 16)   // 0 = stays airborne, 1..NLAND = landing, then NLAND + rank of the contact-slot pattern (1..15)
 struct BrbPerm {
   const int *in;
   uint8_t *key_out;    // [N]

@@ -10,7 +10,7 @@ import helpers
 from balance_robot_b200 import mjcf, model
 from oracle import ref
 
-GOLD = sorted((pathlib.Path(__file__).parent / "golden").glob("*.npz"))
+GOLD = sorted((pathlib.Path(__file__).parent / "golden").glob("Env*_n*_s*.npz"))
 
 
 @pytest.mark.parametrize("path", GOLD, ids=[p.stem for p in GOLD])

@@ -11,7 +11,7 @@ import parity_checks as pc
 from balance_robot_b200 import make_vec, mjcf, model
 
 pytestmark = pytest.mark.gpu
-GOLD = sorted((pathlib.Path(__file__).parent / "golden").glob("*.npz"))
+GOLD = sorted((pathlib.Path(__file__).parent / "golden").glob("Env*_n*_s*.npz"))
 
 
 class GpuAdapter:
