@@ -657,16 +657,17 @@ BRB_D int env03_detect(const BrbModelConsts &c, const Phys &P, const Blk &B, flo
 // decouples exactly).  A single code path keeps the loop body inside the instruction cache: the first version had
 // separate robot / block / coupled solvers and was fetch-bound (ncu: stall_no_instruction 4.9 per issue, profiles/).
 template <int MAXIT>
-BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&qstale)[4], float (&pstale)[3], Env03Stats &es) {
+BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&qstale)[4], float (&pstale)[3], Env03Stats &es, const unsigned wmask) {
   int sidx = 0, it = 0, nbb = 0, qprev_nc = -1;
-  bool need_setup = true;
+  bool need_setup = true, done = false;   // warp-uniform loop + explicit reconvergence: see phys_run
   float bpos[8][3], bdist[8], bn[3];
   CBSet Q;
   Q.nc = 0; Q.bits = 0xFFFFFFFFu;
   unsigned was = 0u;
   int wasn = -1;
   for (;;) {
-    if (need_setup) {
+    if (!__any_sync(wmask, !done)) break;
+    if (!done && need_setup) {
       phys_setup<true>(c, P);
       const unsigned fresh = P.valid & ~was;
       P.bits |= ((fresh & 1u) ? 0xFu : 0u) | ((fresh & 2u) ? 0xF0u : 0u) | ((fresh & 4u) ? 0xF00u : 0u) | ((fresh & 8u) ? 0xF000u : 0u);
@@ -689,15 +690,17 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
     bool conv = true;
 #ifdef BRB_TRIPSTATS
     {
-      const unsigned act = __activemask();
-      const unsigned nv = __popc(__ballot_sync(act, Q.nc > 0));
-      if ((threadIdx.x & 31u) == (unsigned)(__ffs(act) - 1)) {
+      const unsigned act = __ballot_sync(wmask, !done);
+      const unsigned nv = __popc(__ballot_sync(wmask, !done && Q.nc > 0));
+      if ((threadIdx.x & 31u) == (unsigned)(__ffs(wmask) - 1)) {
         atomicAdd(&g_trip[0], 1ull); atomicAdd(&g_trip[1], (unsigned long long)__popc(act));
         if (nv) { atomicAdd(&g_trip[2], 1ull); atomicAdd(&g_trip[3], (unsigned long long)nv); }
       }
     }
 #endif
-    if (P.valid || B.nc > 0 || Q.nc > 0) {
+    __syncwarp(wmask);
+    if (done) {
+    } else if (P.valid || B.nc > 0 || Q.nc > 0) {
       coupled_solve_fast(c, P, B, Q, ar, ab);
       es.csolves++;
       const unsigned nr = P.valid ? phys_active_set<true>(c, P, ar, P.bits) : P.bits;
@@ -737,7 +740,8 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
       ar[7] = c.minv_blk[3] * f[1] + c.minv_blk[6] * f[3] + c.minv_blk[8] * f[6] + c.minv_blk[9] * f[7];
       ab[0] = 0.f; ab[1] = 0.f; ab[2] = -c.grav; ab[3] = 0.f; ab[4] = 0.f; ab[5] = 0.f;
     }
-    if (conv) {
+    __syncwarp(wmask);
+    if (!done && conv) {
       if (sidx == nsub - 1) {
 #pragma unroll
         for (int k = 0; k < 4; k++) qstale[k] = P.q[k];
@@ -748,7 +752,7 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
       phys_finalize(c, P, ar[0], ar[1], ar[2], P.ex[0] * ar[3] + P.ex[1] * ar[4] + P.ex[2] * ar[5],
                     P.ey[0] * ar[3] + P.ey[1] * ar[4] + P.ey[2] * ar[5], P.ez[0] * ar[3] + P.ez[1] * ar[4] + P.ez[2] * ar[5], ar[6], ar[7]);
       blk_finalize(c, B, ab);
-      if (++sidx >= nsub) break;
+      if (++sidx >= nsub) done = true;
       need_setup = true;
     }
   }
@@ -825,7 +829,7 @@ BRB_D void reset_env03(const BrbState &S, long long i, const double *u, float o[
 BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long long i, const float *__restrict__ actions,
                       float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done,
                       uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs, float *__restrict__ ep_return_out,
-                      int32_t *__restrict__ ep_len_out, const double *__restrict__ replay_u, unsigned stat[12]) {
+                      int32_t *__restrict__ ep_len_out, const double *__restrict__ replay_u, unsigned stat[12], const unsigned wmask) {
   const long long N = S.n;
   double qvel[14], xq[4];
   for (int k = 0; k < 14; k++) qvel[k] = S.qvel[k * N + i];
@@ -864,13 +868,12 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
   KF qprev[4];
   float pstale[3];
   Env03Stats es = {0u, 0u, 0u, 0u, 0u, 0u};
-  phys03_run<BRB_MAXIT>(c, st, B, c.frame_skip, qprev, pstale, es);
+  phys03_run<BRB_MAXIT>(c, st, B, c.frame_skip, qprev, pstale, es, wmask);
   stat[0] = c.frame_skip; stat[1] = st.n_contact; stat[2] = st.n_solve; stat[3] = st.n_nonconv; stat[7] = st.n_slots;
   stat[8] = es.coupled; stat[9] = es.blk_contact; stat[10] = es.fallback; stat[11] = es.csolves;
   {
-    const float drop = 0.005f * (fabsf(st.v[2].s) + 0.12f * (fabsf(st.w[0].s) + fabsf(st.w[1].s) + fabsf(st.w[2].s))) + 0.0005f;
-    const bool far = phys_clearance(c, st) > drop;
-    stat[6] = (st.valid == 0u && far) ? 0u : 1u + group_rank(st.valid);
+    stat[6] = (st.valid == 0u) ? airborne_key(c, st.q[0].s, st.q[1].s, st.q[2].s, st.q[3].s, st.p[2].s, st.v[2].s, st.w[0].s, st.w[1].s, st.w[2].s)
+                               : BRB_NLAND + group_rank(st.valid);
     // robots whose block was touching the chassis in the last substep (impacts last ~6 env steps) get their own bucket, so
     // the warps running the coupled assembly are not diluted by robots on the uncoupled path
     if (es.coupled_last) stat[6] = BRB_NGROUPS - 1;

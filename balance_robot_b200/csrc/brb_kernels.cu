@@ -807,7 +807,7 @@ __global__ void __launch_bounds__(BRB_BLOCK, (KIND == BRB_ENV03_V2) ? BRB_MINBLO
   unsigned stat[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const unsigned wmask = __ballot_sync(0xFFFFFFFFu, live);   // lanes of this warp that run a robot
   if (live) {
-    if (KIND == BRB_ENV03_V2) step_env03(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat);
+    if (KIND == BRB_ENV03_V2) step_env03(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat, wmask);
     else step_env<KIND>(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat, wmask);
   }
   if (perm.key_out) {

@@ -56,19 +56,37 @@ _NO_INFO: dict = {}
 class LazyInfoList(list):
     """SB3's `infos`: a real list of dicts, one per env.  Envs that did not finish share one empty dict; the dicts of the
     finished envs (terminal_observation / TimeLimit.truncated / Monitor's episode record) are built on first access, so a
-    step costs O(1) Python work instead of O(#done) when the consumer only looks at a few of them."""
+    step costs one pointer fill of Python work instead of O(#done) dict constructions when the consumer only looks at a
+    few of them.  `idx` is the ascending array of finished env indices (np.flatnonzero)."""
 
     def __init__(self, n, idx, tobs, trunc, epr, epl, t):
         super().__init__([_NO_INFO] * n)
-        self._pending = {int(i): k for k, i in enumerate(idx)}
-        self._src = (tobs, trunc, epr, epl, t)
+        self._built = []
+        self.refill(idx, tobs, trunc, epr, epl, t)
 
-    def _build(self, i):
-        k = self._pending.pop(i)
+    def refill(self, idx, tobs, trunc, epr, epl, t):
+        """Re-use this list for another step: only the entries that were materialised are reset (BalanceVecEnv keeps two
+        of these and alternates, like its pinned output buffers, so creating `infos` is O(1) per step, not O(num_envs))."""
+        for i in self._built:
+            list.__setitem__(self, i, _NO_INFO)
+        self._built = []
+        self._idx = idx
+        self._left = len(idx)          # finished envs whose dict has not been built yet
+        self._src = (tobs, trunc, epr, epl, t)
+        return self
+
+    def _lookup(self, i):
+        """position of env i among the finished envs, or -1"""
+        k = int(np.searchsorted(self._idx, i))
+        return k if k < len(self._idx) and self._idx[k] == i else -1
+
+    def _build(self, i, k):
         tobs, trunc, epr, epl, t = self._src
         d = {"terminal_observation": tobs[k], "TimeLimit.truncated": bool(trunc[k]),
              "episode": {"r": float(epr[k]), "l": int(epl[k]), "t": t}}
         list.__setitem__(self, i, d)
+        self._built.append(i)
+        self._left -= 1
         return d
 
     def __getitem__(self, i):
@@ -76,15 +94,21 @@ class LazyInfoList(list):
             i = int(i)
             if i < 0:
                 i += len(self)
-            if i in self._pending:
-                return self._build(i)
-        elif self._pending:
+            d = list.__getitem__(self, i)
+            if d is _NO_INFO and self._left:
+                k = self._lookup(i)
+                if k >= 0:
+                    return self._build(i, k)
+            return d
+        if self._left:
             self._materialise()
         return list.__getitem__(self, i)
 
     def _materialise(self):
-        for i in list(self._pending):
-            self._build(i)
+        if self._left:
+            for k, i in enumerate(self._idx):
+                if list.__getitem__(self, int(i)) is _NO_INFO:
+                    self._build(int(i), k)
 
     def __iter__(self):
         self._materialise()
@@ -213,10 +237,14 @@ class BalanceVecEnv:
                                             hb["epr"].data_ptr(), hb["epl"].data_ptr()), "brb_env_step_host")
             done = hb["done"].numpy().astype(bool)
             idx = np.flatnonzero(done)
-            infos = LazyInfoList(self.num_envs, idx, hb["tobs"].numpy()[idx], hb["trunc"].numpy()[idx], hb["epr"].numpy()[idx],
-                                 hb["epl"].numpy()[idx], round(time.time() - self._t0, 6))
-            # the returned arrays are views of this step's pinned buffers; the other buffer set is used by the next step,
-            # so they stay valid for one more step() (SB3 copies them into its rollout buffer right away)
+            src = (idx, hb["tobs"].numpy()[idx], hb["trunc"].numpy()[idx], hb["epr"].numpy()[idx], hb["epl"].numpy()[idx],
+                   round(time.time() - self._t0, 6))
+            if "infos" in hb:
+                infos = hb["infos"].refill(*src)
+            else:
+                infos = hb["infos"] = LazyInfoList(self.num_envs, *src)
+            # the returned arrays (and the infos list) belong to this step's buffer set; the other set is used by the next
+            # step, so they stay valid for one more step() (SB3 copies them into its rollout buffer right away)
             return hb["obs"].numpy(), hb["rew"].numpy(), done, infos
         a = self._actions
         if not isinstance(a, torch.Tensor):

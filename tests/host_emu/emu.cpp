@@ -57,7 +57,7 @@ template <int KIND> static void step_all(Emu *e, const float *actions, float *ob
                                          float *tobs, float *epr, int32_t *epl, const double *replay) {
   for (long long i = 0; i < e->S.n; i++) {
     unsigned stat[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (KIND == BRB_ENV03_V2) step_env03(e->c, e->S, i, actions, obs, reward, done, trunc, tobs, epr, epl, replay, stat);
+    if (KIND == BRB_ENV03_V2) step_env03(e->c, e->S, i, actions, obs, reward, done, trunc, tobs, epr, epl, replay, stat, 1u);
     else step_env<KIND>(e->c, e->S, i, actions, obs, reward, done, trunc, tobs, epr, epl, replay, stat, 1u);
     for (int k = 0; k < 6; k++) e->stats[k] += stat[k];
     e->stats[BRB_STAT_CONTACT_SLOTS] += stat[7];
