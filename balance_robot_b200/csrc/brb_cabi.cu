@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
@@ -46,7 +47,8 @@ struct BrbEnv {
   cudaStream_t host_stream;
 };
 
-#define CK(x) do { if ((x) != cudaSuccess) { cudaGetLastError(); return BRB_ECUDA; } } while (0)
+// BRB_DEBUG=1 in the environment prints the CUDA error string behind a BRB_ECUDA status
+#define CK(x) do { cudaError_t ck_ = (x); if (ck_ != cudaSuccess) { if (getenv("BRB_DEBUG")) fprintf(stderr, "[brb] %s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(ck_)); cudaGetLastError(); return BRB_ECUDA; } } while (0)
 
 extern "C" int brb_version(void) { return 100; }
 

@@ -786,13 +786,13 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
 #include "brb_env03.cuh"
 
 #ifndef BRB_HOST_EMU
-#ifdef BRB_MAXNREG
-#define BRB_STEP_BOUNDS __maxnreg__(BRB_MAXNREG)
+#ifdef BRB_MAXNREG   // kernel-tuning experiments: explicit register cap instead of the occupancy hint
+#define BRB_STEP_BOUNDS(KIND) __maxnreg__(BRB_MAXNREG)
 #else
-#define BRB_STEP_BOUNDS __launch_bounds__(BRB_BLOCK, BRB_MINBLOCKS)
+#define BRB_STEP_BOUNDS(KIND) __launch_bounds__(BRB_BLOCK, (KIND == BRB_ENV03_V2) ? BRB_MINBLOCKS_ENV03 : BRB_MINBLOCKS)
 #endif
 template <int KIND>
-__global__ void __launch_bounds__(BRB_BLOCK, (KIND == BRB_ENV03_V2) ? BRB_MINBLOCKS_ENV03 : BRB_MINBLOCKS) brb_step_kernel(const __grid_constant__ BrbModelConsts c, const BrbState S, const BrbPerm perm,
+__global__ void BRB_STEP_BOUNDS(KIND) brb_step_kernel(const __grid_constant__ BrbModelConsts c, const BrbState S, const BrbPerm perm,
                                                 const float *__restrict__ actions, float *__restrict__ obs,
                                                 float *__restrict__ reward, uint8_t *__restrict__ done,
                                                 uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs,
