@@ -35,8 +35,8 @@ ALG_FLOP_PER_ENV_STEP = FLOP_PER_SUBSTEP_CONTACT * FRAME_SKIP          # 9.25e5 
 ALG_BYTES_PER_ENV_STEP = 290.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum of brb_step_kernel<1> from the committed `ncu --set full` capture
-# (profiles/r1_step_kernel_ncu_raw.csv: 13,964,288 + 5,632 bytes for 65,536 robots) -> bytes per robot-step
-NCU_DRAM_BYTES_PER_ENV_STEP = (13964288 + 5632) / 65536
+# (profiles/r1_step_kernel_ncu_raw.csv: 13,971,968 + 5,376 bytes for 65,536 robots) -> bytes per robot-step
+NCU_DRAM_BYTES_PER_ENV_STEP = (13971968 + 5376) / 65536
 
 
 def parse_args():
@@ -44,6 +44,9 @@ def parse_args():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=200)
     ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--spinup", type=int, default=192,
+                    help="untimed steps before the warm-up: all robots start 2 cm in the air (Q11), so the first ~13 steps after "
+                         "reset_all are cheap free fall; the spin-up brings the population to its stationary airborne/grounded mix")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--envs-per-gpu", type=int, default=65536)
     ap.add_argument("--env", default=ENV_ID)
@@ -63,7 +66,8 @@ def workload_config(args, world):
             "frame_skip": FRAME_SKIP,
             "actions": "U(-1,1)^2, torch.Generator(cuda).manual_seed(1234)" if args.actions == "random"
             else "on-device MlpPolicy (6-64-64-2 tanh, random init seed 0) sampled every step inside the timed region",
-            "cache": "L2 flushed (256 MiB write) before every timed step", "sharding": f"env-dp{world}"}
+            "cache": "L2 flushed (256 MiB write) before every timed step", "sharding": f"env-dp{world}",
+            "spinup_steps": args.spinup}
 
 
 # ------------------------------------------------------------------------------------------------ CPU legs (oracle)
@@ -79,6 +83,7 @@ def cpu_leg(args, steps, warmup, threads):
     _, ur = ref.philox_draws(args.seed, 0, n, 0)
     rv.reset(ur)
     rng = np.random.default_rng(1234)
+    warmup += args.spinup          # same untimed spin-up to the stationary airborne/grounded mix as the GPU arm
     draws = [ref.philox_draws(args.seed, 0, n, k + 1) for k in range(warmup + steps)]
     acts = rng.uniform(-1, 1, (warmup + steps, n, 2)).astype(np.float32)
     for k in range(warmup):
@@ -96,7 +101,7 @@ def run_reference(args, rank, world):
         return
     threads = args.cpu_threads or (os.cpu_count() or 1)
     value, dt, n = cpu_leg(args, args.steps, args.warmup, threads)
-    sample = f"{n} envs (64 per thread) x {args.steps} steps after {args.warmup} warm-up, same action distribution, replayed Philox draws"
+    sample = f"{n} envs (64 per thread) x {args.steps} steps after {args.spinup} spin-up + {args.warmup} warm-up, same action distribution, replayed Philox draws"
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world), "impl": "reference",
@@ -191,7 +196,7 @@ def run_b200(args, rank, world, local_rank):
             a, _, _ = policy.act(obs_t, generator=gen)
             obs_t = env.step(a.clamp(-1.0, 1.0))[0]
 
-    for k in range(args.warmup):
+    for k in range(args.spinup + args.warmup):
         one_step(k)
     torch.cuda.synchronize(dev)
     stats0 = env.stats()
@@ -232,7 +237,7 @@ def run_b200(args, rank, world, local_rank):
         rng = np.random.default_rng(99 + rank)
         acts_h = [rng.uniform(-1, 1, (n, 2)).astype(np.float32) for _ in range(4)]
         e2e_steps = max(10, min(args.steps, 50))
-        for k in range(3):
+        for k in range(args.spinup + 3):
             env_h.step(acts_h[k % 4])
         if dist is not None:
             dist.barrier()
@@ -289,7 +294,7 @@ def run_b200(args, rank, world, local_rank):
         threads = args.cpu_threads or (os.cpu_count() or 1)
         v, dt, ncpu = cpu_leg(args, 120, 10, threads)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
-                        "sample": f"{ncpu} envs (64 per thread) x 120 steps after 10 warm-up ({dt:.1f} s), fp64 oracle, replayed Philox draws"}
+                        "sample": f"{ncpu} envs (64 per thread) x 120 steps after {args.spinup} spin-up + 10 warm-up ({dt:.1f} s timed), fp64 oracle, replayed Philox draws"}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu_baseline,

@@ -1,0 +1,9 @@
+set -x
+python bench.py > gpurun_out/bench_r1_s3.json 2> gpurun_out/bench_r1_s3.err || exit 1
+B="python bench.py --steps 10 --warmup 5 --no-cpu-baseline --no-e2e"
+$B > gpurun_out/plain_s3.log 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/launches_s3.csv $B > gpurun_out/ncu1_s3.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:brb_step -s 200 -c 1 -f -o gpurun_out/prof_s3 $B > gpurun_out/ncu2_s3.log 2>&1
+ncu -i gpurun_out/prof_s3.ncu-rep --page raw --csv > gpurun_out/raw_s3.csv 2>/dev/null
+ncu -i gpurun_out/prof_s3.ncu-rep --page source --csv > gpurun_out/src_s3.csv 2>/dev/null
+ls -la gpurun_out/ | tail -8
+cat gpurun_out/bench_r1_s3.json
