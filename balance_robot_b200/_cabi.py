@@ -21,12 +21,13 @@ HEADERS = (CSRC / "brb_internal.h", CSRC / "brb_chol8.inc", CSRC / "brb_chol6.in
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]
 
+DONE_ROW_WORDS = 10   # include/brb.h BRB_DONE_ROW_WORDS
 NSTATS = 12
 STAT_NAMES = ("substeps", "contact_substeps", "solves", "nonconverged", "unsupported", "episodes", "env_steps", "contact_slots", "coupled_substeps", "block_contact_substeps", "coupled_fallbacks", "coupled_solves")
 
 EXPORTS = (
     "brb_version", "brb_strerror", "brb_model_create", "brb_model_destroy", "brb_env_create", "brb_env_destroy",
-    "brb_env_reset_all", "brb_env_step", "brb_env_step_host", "brb_env_get_state", "brb_env_set_state",
+    "brb_env_reset_all", "brb_env_step", "brb_env_step_host", "brb_env_step_host_compact", "brb_env_get_state", "brb_env_set_state",
     "brb_env_get_elapsed", "brb_env_get_stats", "brb_env_num_envs", "brb_env_num_launches", "brb_fp32_peak_flops",
 )
 
@@ -78,6 +79,7 @@ def lib() -> C.CDLL:
     L.brb_env_reset_all.argtypes = [vp, vp, vp, vp]
     L.brb_env_step.argtypes = [vp] * 11
     L.brb_env_step_host.argtypes = [vp] * 9
+    L.brb_env_step_host_compact.argtypes = [vp] * 7 + [i64]
     L.brb_env_get_state.argtypes = [vp] * 5
     L.brb_env_set_state.argtypes = [vp] * 4
     L.brb_env_get_elapsed.argtypes = [vp] * 3

@@ -18,6 +18,9 @@ void brb_launch_step(int kind, const BrbModelConsts *c, const BrbState *S, const
 void brb_launch_group(long long n, const uint8_t *key, const unsigned *hist, unsigned *cursor, int *order, unsigned *hist_zero,
                       unsigned *cursor_zero, cudaStream_t stream);
 void brb_launch_reset(int kind, const BrbState *S, float *obs, const double *replay_u, cudaStream_t stream);
+void brb_launch_done_rows(long long n, const uint8_t *done, const uint8_t *truncated, const float *terminal_obs, const float *ep_return,
+                          const int32_t *ep_len, unsigned *block_count, unsigned *block_base, unsigned *ticket, int *n_done,
+                          uint32_t *rows, cudaStream_t stream);
 void brb_launch_get_state(const BrbState *S, double *qpos, double *qvel, double *xquat, cudaStream_t stream);
 void brb_launch_set_state(const BrbState *S, const double *qpos, const double *qvel, cudaStream_t stream);
 void brb_launch_get_elapsed(const BrbState *S, int32_t *out, cudaStream_t stream);
@@ -44,6 +47,10 @@ struct BrbEnv {
   float *d_actions, *d_obs, *d_reward, *d_tobs, *d_epret;
   uint8_t *d_done, *d_trunc;
   int32_t *d_eplen;
+  // finished-episode compaction for brb_env_step_host_compact
+  unsigned *d_blk_count, *d_blk_base, *d_ticket;   // [ceil(N/256)] x 2, [1] ticket followed by [1] n_done
+  uint32_t *d_rows;                                // [N][BRB_DONE_ROW_WORDS]
+  int32_t *h_ndone;                                // pinned
   cudaStream_t host_stream;
 };
 
@@ -100,7 +107,9 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
       align_up(NQ * N * 8), align_up(NV * N * 8), align_up(4 * N * 8), align_up(8 * N * 4), align_up(N * 8), align_up(N * 8),
       align_up(3 * N * 8), align_up(N * 4), align_up(N * 4), align_up(N * 4), align_up(BRB_NSTATS * 8), align_up(N * 4), align_up(N), align_up(4 * 32 * 4),
       // staging
-      align_up(2 * N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(N), align_up(N), align_up(N * 4)};
+      align_up(2 * N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(N), align_up(N), align_up(N * 4),
+      // finished-episode compaction
+      align_up(((N + 255) / 256) * 4), align_up(((N + 255) / 256) * 4), align_up(2 * 4), align_up(N * BRB_DONE_ROW_WORDS * 4)};
   size_t total = 0;
   for (size_t k = 0; k < sizeof(sz) / sizeof(sz[0]); k++) total += sz[k];
   if (cudaMalloc(&e->arena, total) != cudaSuccess) { cudaGetLastError(); free(e); return BRB_ENOMEM; }
@@ -130,6 +139,10 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
   e->d_done = TAKE(uint8_t);
   e->d_trunc = TAKE(uint8_t);
   e->d_eplen = TAKE(int32_t);
+  e->d_blk_count = TAKE(unsigned);
+  e->d_blk_base = TAKE(unsigned);
+  e->d_ticket = TAKE(unsigned);
+  e->d_rows = TAKE(uint32_t);
 #undef TAKE
   e->S.n = n;
   e->S.nq = m->consts.nq;
@@ -141,6 +154,7 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
   e->have_order = 0;
   e->sort_envs = getenv("BRB_NO_SORT") ? 0 : 1;
   if (cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaFree(e->arena); free(e); return BRB_ECUDA; }
+  if (cudaMallocHost(&e->h_ndone, sizeof(int32_t)) != cudaSuccess) { cudaStreamDestroy(e->host_stream); cudaFree(e->arena); free(e); return BRB_ENOMEM; }
   *out = e;
   return BRB_OK;
 }
@@ -149,6 +163,7 @@ extern "C" void brb_env_destroy(BrbEnv *e) {
   if (!e) return;
   cudaSetDevice(e->model->device);
   cudaStreamDestroy(e->host_stream);
+  cudaFreeHost(e->h_ndone);
   cudaFree(e->arena);
   free(e);
 }
@@ -214,6 +229,33 @@ extern "C" int brb_env_step_host(BrbEnv *e, const float *actions, float *obs, fl
   if (ep_return) CK(cudaMemcpyAsync(ep_return, e->d_epret, N * sizeof(float), cudaMemcpyDeviceToHost, s));
   if (ep_len) CK(cudaMemcpyAsync(ep_len, e->d_eplen, N * sizeof(int32_t), cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  return BRB_OK;
+}
+
+extern "C" int brb_env_step_host_compact(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, int32_t *n_done,
+                                         uint32_t *done_rows, int64_t max_rows) {
+  if (!e || !actions || !obs || !n_done || (max_rows > 0 && !done_rows) || max_rows < 0) return BRB_EINVAL;
+  CK(cudaSetDevice(e->model->device));
+  const size_t N = (size_t)e->S.n;
+  cudaStream_t s = e->host_stream;
+  CK(cudaMemcpyAsync(e->d_actions, actions, 2 * N * sizeof(float), cudaMemcpyHostToDevice, s));
+  launch_step(e, e->d_actions, e->d_obs, e->d_reward, e->d_done, e->d_trunc, e->d_tobs, e->d_epret, e->d_eplen, nullptr, s);
+  brb_launch_done_rows(e->S.n, e->d_done, e->d_trunc, e->d_tobs, e->d_epret, e->d_eplen, e->d_blk_count, e->d_blk_base, e->d_ticket,
+                       (int *)(e->d_ticket + 1), e->d_rows, s);
+  e->launches += 2;
+  CK(cudaGetLastError());
+  CK(cudaMemcpyAsync(e->h_ndone, e->d_ticket + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(obs, e->d_obs, 6 * N * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (reward) CK(cudaMemcpyAsync(reward, e->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, s));
+  if (done) CK(cudaMemcpyAsync(done, e->d_done, N, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  const int32_t nd = *e->h_ndone;
+  *n_done = nd;
+  if (nd > max_rows) return BRB_EINVAL;
+  if (nd > 0) {
+    CK(cudaMemcpyAsync(done_rows, e->d_rows, (size_t)nd * BRB_DONE_ROW_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+  }
   return BRB_OK;
 }
 

@@ -871,6 +871,62 @@ __global__ void brb_group_kernel(long long n, const uint8_t *__restrict__ key, c
   if (tid < BRB_NGROUPS) { hist_zero[tid] = 0u; cursor_zero[tid] = 0u; }
 }
 
+// ---- finished-episode records of one step, compacted in ascending env order (host path: only these rows cross PCIe).
+// Row = BRB_DONE_ROW_WORDS 32-bit words: [env index (i32) | terminal_obs[6] (f32) | ep_return (f32) | ep_len (i32) | truncated (i32)].
+// Pass 1: per-CTA counts; the last CTA to arrive scans them into exclusive bases and the total.  Pass 2: rows.
+__global__ void brb_done_count_kernel(long long n, const uint8_t *__restrict__ done, unsigned *__restrict__ block_count,
+                                      unsigned *__restrict__ block_base, unsigned *ticket, int *n_done) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const int cnt = __syncthreads_count(i < n && done[i] != 0);
+  __shared__ bool last;
+  __shared__ unsigned part[256];
+  if (threadIdx.x == 0) {
+    block_count[blockIdx.x] = (unsigned)cnt;
+    __threadfence();
+    last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  const unsigned nb = gridDim.x, per = (nb + blockDim.x - 1) / blockDim.x;
+  const unsigned lo = threadIdx.x * per, hi = min(nb, lo + per);
+  unsigned sum = 0;
+  for (unsigned b = lo; b < hi; b++) sum += ((volatile unsigned *)block_count)[b];
+  part[threadIdx.x] = sum;
+  __syncthreads();
+  for (unsigned o = 1; o < blockDim.x; o <<= 1) {       // inclusive scan of the 256 partial sums
+    const unsigned v = threadIdx.x >= o ? part[threadIdx.x - o] : 0u;
+    __syncthreads();
+    part[threadIdx.x] += v;
+    __syncthreads();
+  }
+  unsigned base = part[threadIdx.x] - sum;
+  for (unsigned b = lo; b < hi; b++) { block_base[b] = base; base += ((volatile unsigned *)block_count)[b]; }
+  if (threadIdx.x == blockDim.x - 1) { *n_done = (int)part[threadIdx.x]; *ticket = 0u; }
+}
+
+__global__ void brb_done_rows_kernel(long long n, const uint8_t *__restrict__ done, const uint8_t *__restrict__ truncated,
+                                     const float *__restrict__ terminal_obs, const float *__restrict__ ep_return,
+                                     const int32_t *__restrict__ ep_len, const unsigned *__restrict__ block_base, uint32_t *__restrict__ rows) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool d = i < n && done[i] != 0;
+  __shared__ unsigned wcount[8];
+  const unsigned lane = threadIdx.x & 31u, w = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xFFFFFFFFu, d);
+  if (lane == 0) wcount[w] = __popc(bal);
+  __syncthreads();
+  if (!d) return;
+  unsigned r = block_base[blockIdx.x] + __popc(bal & ((1u << lane) - 1u));
+  for (unsigned k = 0; k < w; k++) r += wcount[k];
+  uint32_t *row = rows + (size_t)r * BRB_DONE_ROW_WORDS;
+  row[0] = (uint32_t)i;
+#pragma unroll
+  for (int k = 0; k < 6; k++) row[1 + k] = __float_as_uint(terminal_obs[i * 6 + k]);
+  row[7] = __float_as_uint(ep_return[i]);
+  row[8] = (uint32_t)ep_len[i];
+  row[9] = (uint32_t)truncated[i];
+}
+
 template <int KIND>
 __global__ void brb_reset_kernel(const BrbState S, float *__restrict__ obs, const double *__restrict__ replay_u) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -965,6 +1021,14 @@ extern "C" void brb_tripstats(unsigned long long *out) { cudaMemcpyFromSymbol(ou
 extern "C" void brb_launch_group(long long n, const uint8_t *key, const unsigned *hist, unsigned *cursor, int *order, unsigned *hist_zero,
                                  unsigned *cursor_zero, cudaStream_t stream) {
   brb_group_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, key, hist, cursor, order, hist_zero, cursor_zero);
+}
+
+extern "C" void brb_launch_done_rows(long long n, const uint8_t *done, const uint8_t *truncated, const float *terminal_obs, const float *ep_return,
+                                     const int32_t *ep_len, unsigned *block_count, unsigned *block_base, unsigned *ticket, int *n_done,
+                                     uint32_t *rows, cudaStream_t stream) {
+  const unsigned nb = (unsigned)((n + 255) / 256);
+  brb_done_count_kernel<<<nb, 256, 0, stream>>>(n, done, block_count, block_base, ticket, n_done);
+  brb_done_rows_kernel<<<nb, 256, 0, stream>>>(n, done, truncated, terminal_obs, ep_return, ep_len, block_base, rows);
 }
 
 extern "C" void brb_launch_reset(int kind, const BrbState *S, float *obs, const double *replay_u, cudaStream_t stream) {

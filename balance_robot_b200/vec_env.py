@@ -82,7 +82,7 @@ class LazyInfoList(list):
 
     def _build(self, i, k):
         tobs, trunc, epr, epl, t = self._src
-        d = {"terminal_observation": tobs[k], "TimeLimit.truncated": bool(trunc[k]),
+        d = {"terminal_observation": np.array(tobs[k]), "TimeLimit.truncated": bool(trunc[k]),
              "episode": {"r": float(epr[k]), "l": int(epl[k]), "t": t}}
         list.__setitem__(self, i, d)
         self._built.append(i)
@@ -180,9 +180,9 @@ class BalanceVecEnv:
             pin = dict(pin_memory=True)
             self._h_act = torch.zeros((n, 2), dtype=torch.float32, **pin)
             self._hbuf = [dict(obs=torch.zeros((n, 6), dtype=torch.float32, **pin), rew=torch.zeros(n, dtype=torch.float32, **pin),
-                               done=torch.zeros(n, dtype=torch.uint8, **pin), trunc=torch.zeros(n, dtype=torch.uint8, **pin),
-                               tobs=torch.zeros((n, 6), dtype=torch.float32, **pin), epr=torch.zeros(n, dtype=torch.float32, **pin),
-                               epl=torch.zeros(n, dtype=torch.int32, **pin)) for _ in range(2)]
+                               done=torch.zeros(n, dtype=torch.uint8, **pin),
+                               rows=torch.zeros((n, _cabi.DONE_ROW_WORDS), dtype=torch.float32, **pin)) for _ in range(2)]
+            self._h_ndone = torch.zeros(1, dtype=torch.int32, **pin)
             self._flip = 0
         self._actions = None
         self._t0 = time.time()
@@ -232,20 +232,20 @@ class BalanceVecEnv:
             self._h_act.numpy()[...] = a
             self._flip ^= 1
             hb = self._hbuf[self._flip]
-            _cabi.check(L.brb_env_step_host(self._env, self._h_act.data_ptr(), hb["obs"].data_ptr(), hb["rew"].data_ptr(),
-                                            hb["done"].data_ptr(), hb["trunc"].data_ptr(), hb["tobs"].data_ptr(),
-                                            hb["epr"].data_ptr(), hb["epl"].data_ptr()), "brb_env_step_host")
-            done = hb["done"].numpy().astype(bool)
-            idx = np.flatnonzero(done)
-            src = (idx, hb["tobs"].numpy()[idx], hb["trunc"].numpy()[idx], hb["epr"].numpy()[idx], hb["epl"].numpy()[idx],
-                   round(time.time() - self._t0, 6))
+            # finished-episode records arrive compacted (ascending env index): only obs / reward / done are full arrays
+            _cabi.check(L.brb_env_step_host_compact(self._env, self._h_act.data_ptr(), hb["obs"].data_ptr(), hb["rew"].data_ptr(),
+                                                    hb["done"].data_ptr(), self._h_ndone.data_ptr(), hb["rows"].data_ptr(),
+                                                    self.num_envs), "brb_env_step_host_compact")
+            rows = hb["rows"].numpy()[:int(self._h_ndone[0])]
+            ints = rows.view(np.int32)
+            src = (ints[:, 0], rows[:, 1:7], ints[:, 9], rows[:, 7], ints[:, 8], round(time.time() - self._t0, 6))
             if "infos" in hb:
                 infos = hb["infos"].refill(*src)
             else:
                 infos = hb["infos"] = LazyInfoList(self.num_envs, *src)
             # the returned arrays (and the infos list) belong to this step's buffer set; the other set is used by the next
             # step, so they stay valid for one more step() (SB3 copies them into its rollout buffer right away)
-            return hb["obs"].numpy(), hb["rew"].numpy(), done, infos
+            return hb["obs"].numpy(), hb["rew"].numpy(), hb["done"].numpy().view(np.bool_), infos
         a = self._actions
         if not isinstance(a, torch.Tensor):
             a = torch.as_tensor(np.asarray(a, dtype=np.float32))

@@ -243,8 +243,10 @@ def run_b200(args, rank, world, local_rank):
             dist.barrier()
         torch.cuda.synchronize(dev)
         t0 = time.perf_counter()
+        n_done_rows = 0
         for k in range(e2e_steps):
             obs_h, rew_h, done_h, infos_h = env_h.step(acts_h[k % 4])
+            n_done_rows += len(infos_h._idx)
         torch.cuda.synchronize(dev)
         dt = time.perf_counter() - t0
         if dist is not None:
@@ -252,8 +254,10 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t.item())
         e2e = {"value": n * world * e2e_steps / dt, "unit": UNIT, "h2d_bytes_per_step": n * 2 * 4,
-               "d2h_bytes_per_step": n * (6 * 4 + 4 + 1 + 1 + 6 * 4 + 4 + 4), "steps": e2e_steps,
-               "path": "BalanceVecEnv(output='numpy').step -> brb_env_step_host (numpy actions in, numpy obs/reward/done + SB3 infos out)"}
+               "d2h_bytes_per_step": n * (6 * 4 + 4 + 1) + 4 + 40 * n_done_rows // e2e_steps, "steps": e2e_steps,
+               "path": "BalanceVecEnv(output='numpy').step -> brb_env_step_host_compact (numpy actions in; numpy obs/reward/done out in "
+                       "full, finished-episode records (terminal_observation, TimeLimit.truncated, Monitor r/l) compacted on the "
+                       "device, 40 B per finished env; SB3 infos list built lazily)"}
         env_h.close()
 
     if rank != 0:

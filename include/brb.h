@@ -100,6 +100,16 @@ int brb_env_step(BrbEnv *e, const float *actions, float *obs, float *reward, uin
 int brb_env_step_host(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,
                       float *terminal_obs, float *ep_return, int32_t *ep_len);
 
+/* Same step, but the per-episode outputs cross PCIe only for the envs that finished: the device compacts them (ascending
+ * env index) into rows of BRB_DONE_ROW_WORDS 32-bit words
+ *   [env index (i32) | terminal_observation[6] (f32) | ep_return (f32) | ep_len (i32) | TimeLimit.truncated (i32)]
+ * = exactly what SB3's DummyVecEnv / Monitor put into infos[i] of a finished env (sb_rl.py:500-501).  obs / reward / done
+ * are full [N] arrays as above.  *n_done receives the number of rows written to done_rows (capacity max_rows rows;
+ * BRB_EINVAL if more envs finished than fit). */
+#define BRB_DONE_ROW_WORDS 10
+int brb_env_step_host_compact(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, int32_t *n_done,
+                              uint32_t *done_rows, int64_t max_rows);
+
 /* MujocoEnv.set_state / data.qpos, data.qvel access (trajectory checks).  xquat = the (stale, Q1) chassis
  * quaternion the observation functions read; may be NULL. */
 int brb_env_get_state(BrbEnv *e, double *qpos, double *qvel, double *xquat, void *stream);

@@ -17,27 +17,11 @@ print(f"env.step (numpy): {(t1 - t0) / K * 1e3:.3f} ms/step -> {n * K / (t1 - t0
 L = _cabi.lib(); hb = env._hbuf[0]
 t0 = time.perf_counter()
 for k in range(K):
-    L.brb_env_step_host(env._env, env._h_act.data_ptr(), hb["obs"].data_ptr(), hb["rew"].data_ptr(), hb["done"].data_ptr(), hb["trunc"].data_ptr(),
-                        hb["tobs"].data_ptr(), hb["epr"].data_ptr(), hb["epl"].data_ptr())
+    L.brb_env_step_host_compact(env._env, env._h_act.data_ptr(), hb["obs"].data_ptr(), hb["rew"].data_ptr(), hb["done"].data_ptr(),
+                                env._h_ndone.data_ptr(), hb["rows"].data_ptr(), n)
 t1 = time.perf_counter()
-print(f"brb_env_step_host only: {(t1 - t0) / K * 1e3:.3f} ms/step")
-t0 = time.perf_counter()
-for k in range(K):
-    L.brb_env_step_host(env._env, env._h_act.data_ptr(), hb["obs"].data_ptr(), None, None, None, None, None, None)
-t1 = time.perf_counter()
-print(f"brb_env_step_host, obs only: {(t1 - t0) / K * 1e3:.3f} ms/step")
-a = np.zeros((n, 2), np.float32)
+print(f"brb_env_step_host_compact only: {(t1 - t0) / K * 1e3:.3f} ms/step")
 t0 = time.perf_counter()
 for k in range(K):
     env._h_act.numpy()[...] = acts[k % 8]
 t1 = time.perf_counter(); print(f"copy actions into pinned: {(t1 - t0) / K * 1e3:.3f} ms")
-t0 = time.perf_counter()
-for k in range(K):
-    done = hb["done"].numpy().astype(bool); idx = np.flatnonzero(done)
-    x = (hb["tobs"].numpy()[idx], hb["trunc"].numpy()[idx], hb["epr"].numpy()[idx], hb["epl"].numpy()[idx])
-t1 = time.perf_counter(); print(f"done/flatnonzero/gathers: {(t1 - t0) / K * 1e3:.3f} ms  (#done {len(idx)})")
-from balance_robot_b200.vec_env import LazyInfoList
-t0 = time.perf_counter()
-for k in range(K):
-    infos = LazyInfoList(n, idx, *x, 0.0)
-t1 = time.perf_counter(); print(f"LazyInfoList: {(t1 - t0) / K * 1e3:.3f} ms")

@@ -150,7 +150,7 @@ def test_replay_and_shard_invariance():
 
 
 def test_numpy_mode_matches_torch_mode_and_sb3_info_contract():
-    n = 256
+    n = 1000          # not a multiple of the compaction kernels' 256-thread CTAs
     a = make_vec("Env01-v2", n, seed=9)
     b = make_vec("Env01-v2", n, seed=9, output="numpy")
     oa, ob = a.reset(), b.reset()
@@ -167,9 +167,41 @@ def test_numpy_mode_matches_torch_mode_and_sb3_info_contract():
             seen_done += 1
             assert set(i2[k]) == {"terminal_observation", "TimeLimit.truncated", "episode"}
             assert i2[k]["terminal_observation"].shape == (6,) and i2[k]["episode"]["l"] >= 1
-            assert i1[int(k)]["episode"]["l"] == i2[k]["episode"]["l"]
+            assert i1[int(k)]["episode"]["l"] == i2[k]["episode"]["l"] and i1[int(k)]["episode"]["r"] == i2[k]["episode"]["r"]
+            assert np.array_equal(i1[int(k)]["terminal_observation"], i2[k]["terminal_observation"])
+            assert i1[int(k)]["TimeLimit.truncated"] == i2[k]["TimeLimit.truncated"]
         assert all(i2[k] == {} for k in np.flatnonzero(~d2)[:5])
     assert seen_done > 0          # Q3: 12.8 % of v2 episodes end at their first step
+    a.close(); b.close()
+
+
+def test_host_step_compact_equals_full_host_step():
+    """brb_env_step_host (every per-episode array in full) and brb_env_step_host_compact (finished envs only) on twin envs."""
+    import ctypes as C
+    from balance_robot_b200 import _cabi
+    n = 70000
+    a = make_vec("Env01-v2", n, seed=4, output="numpy")
+    b = make_vec("Env01-v2", n, seed=4, output="numpy")
+    a.reset(); b.reset()
+    L = _cabi.lib()
+    obs = np.zeros((n, 6), np.float32); rew = np.zeros(n, np.float32); done = np.zeros(n, np.uint8); trunc = np.zeros(n, np.uint8)
+    tobs = np.zeros((n, 6), np.float32); epr = np.zeros(n, np.float32); epl = np.zeros(n, np.int32)
+    rng = np.random.default_rng(1)
+    total = 0
+    for k in range(20):
+        act = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        _cabi.check(L.brb_env_step_host(a._env, act.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data, trunc.ctypes.data,
+                                        tobs.ctypes.data, epr.ctypes.data, epl.ctypes.data), "brb_env_step_host")
+        o2, r2, d2, infos = b.step(act)
+        assert np.array_equal(obs, o2) and np.array_equal(rew, r2) and np.array_equal(done.astype(bool), d2)
+        idx = np.flatnonzero(done)
+        assert np.array_equal(idx, infos._idx)
+        total += len(idx)
+        for i in idx[:: max(1, len(idx) // 50)]:
+            d = infos[int(i)]
+            assert np.array_equal(d["terminal_observation"], tobs[i]) and d["episode"] == {"r": float(epr[i]), "l": int(epl[i]), "t": d["episode"]["t"]}
+            assert d["TimeLimit.truncated"] == bool(trunc[i])
+    assert total > 1000
     a.close(); b.close()
 
 
