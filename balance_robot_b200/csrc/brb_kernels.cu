@@ -301,7 +301,7 @@ BRB_D void phys_setup(const BrbModelConsts &c, Phys &P) {
   const float irho = rsqrtf(fmaxf(rho2, 1e-30f));
   const float rho = rho2 * irho;
   // oz*nz - rad*rho without cancellation when upright: (oz-rad) nz + rad (nz - rho), nz - rho = -ny^2/(nz+rho)
-  const float diff = (n2 > 0.f) ? -(n1 * n1) / (n2 + rho) : (n2 - rho);
+  const float diff = (n2 > 0.f) ? -__fdividef(n1 * n1, n2 + rho) : (n2 - rho);   // 2 ulp of a term that is <= 1e-2 of the height
   const float hgt = ((P.p[2].s - c.zfloor) - P.p[2].c) - c.zfloor_lo;
   const float common = hgt + (c.oz - c.rad) * n2 + c.rad * diff;
   const float anx = fabsf(n0);
@@ -456,12 +456,11 @@ BRB_D void phys_solve(const BrbModelConsts &c, Phys &P, unsigned bits, float (&a
 BRB_D void phys_finalize(const BrbModelConsts &c, Phys &P, float avx, float avy, float avz, float ab0, float ab1, float ab2, float a6, float a7) {
   {
     // a+ = (M + h Dv)^-1 M a = a - Wm (Cinv + G)^-1 [a6; a7]   (Woodbury on the two wheel dofs; Wm touches uy, wx, sL, sR)
+    // (Cinv + G)^-1 depends only on which servos sit on their forcerange: four host-computed 2x2 inverses (constant bank)
     const bool skip = (c.flags & BRB_FLAG_ACTDERIV_SKIP_CLAMPED) != 0;
-    const float cL = (skip && P.clampL) ? c.impl_cinv_damp : c.impl_cinv_full;
-    const float cR = (skip && P.clampR) ? c.impl_cinv_damp : c.impl_cinv_full;
-    const float k00 = cL + c.impl_G[0], k01 = c.impl_G[1], k11 = cR + c.impl_G[2];
-    const float idet = 1.f / (k00 * k11 - k01 * k01);
-    const float y0 = (k11 * a6 - k01 * a7) * idet, y1 = (k00 * a7 - k01 * a6) * idet;
+    const int ci = skip ? ((P.clampL ? 1 : 0) | (P.clampR ? 2 : 0)) : 0;
+    const float i00 = c.impl_Kinv[ci][0], i01 = c.impl_Kinv[ci][1], i11 = c.impl_Kinv[ci][2];
+    const float y0 = i00 * a6 + i01 * a7, y1 = i01 * a6 + i11 * a7;
     const float duy = c.impl_W[0] * y0 + c.impl_W[1] * y1;      // chassis-frame y component of the linear correction
     avx -= P.ey[0] * duy; avy -= P.ey[1] * duy; avz -= P.ey[2] * duy;
     ab0 -= c.impl_W[2] * y0 + c.impl_W[3] * y1;

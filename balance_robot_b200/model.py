@@ -47,6 +47,8 @@ class BrbModelConsts(C.Structure):
         ("mu", C.c_float), ("D", C.c_float), ("Kimp", C.c_float), ("Bdamp", C.c_float),
         # implicitfast: a+ = a - Wm (Cinv + G)^-1 [aL; aR]
         ("impl_W", C.c_float * 8), ("impl_G", C.c_float * 3), ("impl_cinv_full", C.c_float), ("impl_cinv_damp", C.c_float),
+        # (Cinv + G)^-1 as (i00, i01, i11) for the four servo clamp states: index = clampL + 2 clampR
+        ("impl_Kinv", C.c_float * 3 * 4),
         ("chassis_half", C.c_float * 3), ("chassis_pos", C.c_float * 3),
         ("frame_skip", C.c_int), ("max_episode_steps", C.c_int), ("env_kind", C.c_int), ("flags", C.c_int),
         ("pp", C.c_float * 8 * 3),
@@ -242,6 +244,11 @@ def compile_model(spec: ModelSpec, env_kind: int, max_episode_steps: int, frame_
     c.impl_G[:] = [Minv[6, 6], Minv[6, 7], Minv[7, 7]]
     c.impl_cinv_damp = 1.0 / (h * damping) if damping > 0 else 3.0e38
     c.impl_cinv_full = 1.0 / (h * (damping + a0.kv))
+    cinv = (1.0 / (h * (damping + a0.kv)), 1.0 / (h * damping) if damping > 0 else 3.0e38)     # servo active / on its forcerange (A.9)
+    for ci in range(4):
+        k00, k01, k11 = cinv[ci & 1] + Minv[6, 6], Minv[6, 7], cinv[ci >> 1] + Minv[7, 7]
+        det = k00 * k11 - k01 * k01
+        c.impl_Kinv[ci][:] = [k11 / det, -k01 / det, k00 / det]
     chassis_geoms = [g for g in spec.geoms if g.body == chassis and g.type == GEOM_BOX]
     if len(chassis_geoms) == 1:
         c.chassis_half[:] = chassis_geoms[0].size

@@ -57,6 +57,7 @@ typedef struct BrbModelConsts {
   float damping, kv, ctrl_lo, ctrl_hi, frc_lo, frc_hi;
   float mu, D, Kimp, Bdamp;
   float impl_W[8], impl_G[3], impl_cinv_full, impl_cinv_damp;
+  float impl_Kinv[4][3]; /* (Cinv + G)^-1 = (i00, i01, i11) per servo clamp state, index = clampL + 2 clampR */
   float chassis_half[3], chassis_pos[3];
   int frame_skip, max_episode_steps, env_kind, flags;
   /* Env03-v2 only.  pp[k] = {mu, K, B, D1, d0, d1, width, margin} of the dynamic pairs k = 0 wheel-floor, 1 block-floor,

@@ -8,6 +8,7 @@
 #include <math.h>
 #include <stdint.h>
 static inline float rsqrtf(float x) { return 1.0f / sqrtf(x); }
+static inline float __fdividef(float a, float b) { return a / b; }
 // one robot per call on the host: the warp-level votes of the per-lane state machine degenerate
 #define __any_sync(mask, pred) (pred)
 #define __syncwarp(mask) ((void)0)
