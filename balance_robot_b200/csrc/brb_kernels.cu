@@ -352,6 +352,21 @@ BRB_D unsigned phys_active_set(const BrbModelConsts &c, const Phys &P, const flo
   return contact_bits<0>(c, P, a, prev, mu) | contact_bits<1>(c, P, a, prev, mu) | contact_bits<2>(c, P, a, prev, mu) | contact_bits<3>(c, P, a, prev, mu);
 }
 
+// ---- S_c = Pi' W_c Pi for the 16 pyramid-row patterns b of a contact: {Szz, Syz, Sxz, Syy, Sxx} (D folded in when it is a
+//      model constant; unit D for Env03-v2's position-dependent impedance).  One copy per CTA in shared memory.
+#ifdef BRB_HOST_EMU
+static float g_stab[16 * 5];
+#else
+__shared__ float g_stab[16 * 5];
+#endif
+BRB_D void stab_fill(const BrbModelConsts &c, bool vi, int idx) {
+  const unsigned b = (unsigned)idx / 5u, j = (unsigned)idx % 5u;
+  const float b0 = (float)(b & 1u), b1 = (float)((b >> 1) & 1u), b2 = (float)((b >> 2) & 1u), b3 = (float)((b >> 3) & 1u);
+  const float Dc = vi ? 1.f : c.D, muc = vi ? c.pp[0][0] : c.mu;
+  const float Dm = Dc * muc, Dmm = Dm * muc;
+  g_stab[idx] = j == 0 ? Dc * (b0 + b1 + b2 + b3) : j == 1 ? Dm * (b0 - b1) : j == 2 ? -Dm * (b2 - b3) : j == 3 ? Dmm * (b0 + b1) : Dmm * (b2 + b3);
+}
+
 // ---- H += P_c' S P_c, r -= P_c' S yhat-ish for one contact; S = Pi' W_c Pi in world axes:
 //      Sxx = W22, Syy = W11, Szz = W00, Syz = W01, Sxz = -W02, Sxy = 0
 template <int CI, bool VI>
@@ -362,11 +377,11 @@ BRB_D void contact_assemble(const BrbModelConsts &c, const Phys &P, unsigned bit
 #endif
   if ((P.valid & (1u << CI)) && b) {
     constexpr int kw = 6 + (CI >> 1);
-    const float b0 = (float)(b & 1u), b1 = (float)((b >> 1) & 1u), b2 = (float)((b >> 2) & 1u), b3 = (float)((b >> 3) & 1u);
-    const float Dc = VI ? P.cD[CI] : c.D, muc = VI ? c.pp[0][0] : c.mu;
-    const float Dm = Dc * muc, Dmm = Dm * muc;
-    const float Szz = Dc * (b0 + b1 + b2 + b3), Syz = Dm * (b0 - b1), Sxz = -Dm * (b2 - b3);
-    const float Syy = Dmm * (b0 + b1), Sxx = Dmm * (b2 + b3);
+    // S for this row pattern from the 16-entry table in shared memory (stab_fill): 5 LDS on the otherwise idle LSU pipe
+    // instead of ~25 bit-to-float conversions and multiplies on the FP32 pipe
+    const float *t = g_stab + 5 * b;
+    float Szz = t[0], Syz = t[1], Sxz = t[2], Syy = t[3], Sxx = t[4];
+    if (VI) { const float Dc = P.cD[CI]; Szz *= Dc; Syz *= Dc; Sxz *= Dc; Syy *= Dc; Sxx *= Dc; }
     const float rx = P.cr[CI][0], ry = P.cr[CI][1], rz = P.cr[CI][2];
     const float wx = P.cw[CI][0], wy = P.cw[CI][1], wz = P.cw[CI][2];
     // columns of P: e_x e_y e_z | cx=(0,-rz,ry) cy=(rz,0,-rx) cz=(-ry,rx,0) | w ;  T_j = S p_j
@@ -805,6 +820,8 @@ __global__ void BRB_STEP_BOUNDS(KIND) brb_step_kernel(const __grid_constant__ Br
   const long long i = live ? (perm.in ? (long long)perm.in[tid] : tid) : 0;
   unsigned stat[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const unsigned wmask = __ballot_sync(0xFFFFFFFFu, live);   // lanes of this warp that run a robot
+  if (threadIdx.x < 16 * 5) stab_fill(c, KIND == BRB_ENV03_V2, threadIdx.x);
+  __syncthreads();
   if (live) {
     if (KIND == BRB_ENV03_V2) step_env03(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat, wmask);
     else step_env<KIND>(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat, wmask);

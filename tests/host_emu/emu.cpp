@@ -55,6 +55,7 @@ extern "C" void emu_reset(Emu *e, float *obs, const double *replay) {
 }
 template <int KIND> static void step_all(Emu *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *trunc,
                                          float *tobs, float *epr, int32_t *epl, const double *replay) {
+  for (int k = 0; k < 16 * 5; k++) stab_fill(e->c, KIND == BRB_ENV03_V2, k);     // the kernel's per-CTA shared-memory table
   for (long long i = 0; i < e->S.n; i++) {
     unsigned stat[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     if (KIND == BRB_ENV03_V2) step_env03(e->c, e->S, i, actions, obs, reward, done, trunc, tobs, epr, epl, replay, stat, 1u);
