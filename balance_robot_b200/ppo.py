@@ -173,11 +173,12 @@ class PPO:
             done_f = done.to(torch.float32)
             rew = rew.clone()
             # TimeLimit bootstrap: reward += gamma * V(terminal_observation) where the episode was truncated
-            trunc = infos.truncated.to(torch.bool) if hasattr(infos, "truncated") else None
-            if trunc is not None and bool(trunc.any()):
+            # (evaluated for every env and masked: a `trunc.any()` test would put a host sync into every step of the rollout;
+            # terminal_observation rows of envs that never finished are zeros, so the masked product is finite)
+            if hasattr(infos, "truncated"):
                 with torch.no_grad():
                     tv = self.policy.value(infos.terminal_observation)
-                rew = rew + cfg.gamma * tv * trunc.to(rew.dtype)
+                rew = rew + cfg.gamma * tv * infos.truncated.to(rew.dtype)
             b["rewards"][t].copy_(rew)
             b["dones"][t].copy_(done_f)
             if hasattr(infos, "episode_return"):
