@@ -63,6 +63,55 @@ class MlpPolicy(nn.Module):
         var = torch.exp(2 * log_std)
         return (-((actions - mean) ** 2) / (2 * var) - log_std - 0.5 * math.log(2 * math.pi)).sum(-1)
 
+    def packed_parameters(self):
+        """The parameters in the order of the flat block the CUDA kernels read (include/brb.h: SB3 state-dict order)."""
+        return (self.mlp_extractor.policy_net[0].weight, self.mlp_extractor.policy_net[0].bias,
+                self.mlp_extractor.policy_net[2].weight, self.mlp_extractor.policy_net[2].bias,
+                self.mlp_extractor.value_net[0].weight, self.mlp_extractor.value_net[0].bias,
+                self.mlp_extractor.value_net[2].weight, self.mlp_extractor.value_net[2].bias,
+                self.action_net.weight, self.action_net.bias, self.value_net.weight, self.value_net.bias, self.log_std)
+
+    def pack_params(self) -> torch.Tensor:
+        """Flat fp32 parameter block = the layout brb_policy_act / brb_ppo_grad read."""
+        return torch.cat([p.detach().reshape(-1) for p in self.packed_parameters()]).float().contiguous()
+
+    @torch.no_grad()
+    def act_fused(self, obs, deterministic: bool = False, generator: Optional[torch.Generator] = None, params: Optional[torch.Tensor] = None):
+        """act() as ONE CUDA launch (csrc/brb_policy.cu): both towers, the Gaussian sample, log-prob, value and the clipped
+        copy of the action for the env.  Returns (actions, values, log_prob, clipped_actions).  `params` = pack_params()
+        (pass it when the weights do not change between calls, as during a rollout)."""
+        import ctypes as C
+        from . import _cabi
+        if not obs.is_cuda:
+            raise _cabi.BrbError("act_fused runs on CUDA tensors only")
+        if self.action_net.in_features != 64 or self.action_net.out_features != 2 or obs.shape[-1] != 6:
+            raise _cabi.BrbError("act_fused is built for the 6-64-64-2 MlpPolicy")
+        params = self.pack_params() if params is None else params
+        assert params.numel() == _cabi.POLICY_NPARAM and params.is_cuda
+        obs = obs.to(torch.float32).contiguous()
+        n = obs.shape[0]
+        noise = None if deterministic else torch.randn((n, 2), device=obs.device, dtype=torch.float32, generator=generator)
+        actions = torch.empty((n, 2), device=obs.device); clipped = torch.empty((n, 2), device=obs.device)
+        values = torch.empty(n, device=obs.device); logp = torch.empty(n, device=obs.device)
+        with torch.cuda.device(obs.device):
+            _cabi.check(_cabi.lib().brb_policy_act(params.data_ptr(), obs.data_ptr(), noise.data_ptr() if noise is not None else None, n,
+                                                   actions.data_ptr(), clipped.data_ptr(), values.data_ptr(), logp.data_ptr(),
+                                                   C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)), "brb_policy_act")
+        return actions, values, logp, clipped
+
+    @torch.no_grad()
+    def value_fused(self, obs, params: Optional[torch.Tensor] = None):
+        """value() through the fused kernel (critic tower only)."""
+        import ctypes as C
+        from . import _cabi
+        params = self.pack_params() if params is None else params
+        obs = obs.to(torch.float32).contiguous()
+        values = torch.empty(obs.shape[0], device=obs.device)
+        with torch.cuda.device(obs.device):
+            _cabi.check(_cabi.lib().brb_policy_act(params.data_ptr(), obs.data_ptr(), None, obs.shape[0], None, None, values.data_ptr(), None,
+                                                   C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)), "brb_policy_act")
+        return values
+
     @torch.no_grad()
     def act(self, obs, deterministic: bool = False, generator: Optional[torch.Generator] = None):
         mean, log_std = self._dist(obs)
@@ -128,6 +177,8 @@ class PPO:
         self.optimizer = torch.optim.Adam(self.policy.parameters(), lr=config.learning_rate, eps=config.adam_eps)
         self.gen = torch.Generator(device=self.device).manual_seed(config.seed * 1000003 + rank)
         self.num_timesteps = 0
+        self.fused_update = True      # CUDA: minibatch forward + loss + backward through brb_ppo_grad (False: autograd)
+        self._gflat = None
         self._obs = None
         self.ep_stats = {"return_sum": 0.0, "len_sum": 0.0, "count": 0.0}
         n, T = env.num_envs, config.n_steps
@@ -163,13 +214,19 @@ class PPO:
         ep_ret = torch.zeros((), device=self.device, dtype=torch.float64)
         ep_len = torch.zeros((), device=self.device, dtype=torch.float64)
         ep_cnt = torch.zeros((), device=self.device, dtype=torch.float64)
+        fused = self.device.type == "cuda" and self.policy.action_net.in_features == 64
+        params = self.policy.pack_params() if fused else None      # the weights do not change during a rollout
         for t in range(cfg.n_steps):
-            actions, values, logp = self.policy.act(self._obs, generator=self.gen)
+            if fused:       # one launch: towers + sample + log-prob + value + clipped copy (csrc/brb_policy.cu)
+                actions, values, logp, clipped = self.policy.act_fused(self._obs, generator=self.gen, params=params)
+            else:
+                actions, values, logp = self.policy.act(self._obs, generator=self.gen)
+                clipped = actions.clamp(-1.0, 1.0)                     # SB3 clips for the env only
             b["obs"][t].copy_(self._obs)
             b["actions"][t].copy_(actions)
             b["values"][t].copy_(values)
             b["logp"][t].copy_(logp)
-            obs, rew, done, infos = env.step(actions.clamp(-1.0, 1.0))      # SB3 clips for the env only
+            obs, rew, done, infos = env.step(clipped)
             done_f = done.to(torch.float32)
             rew = rew.clone()
             # TimeLimit bootstrap: reward += gamma * V(terminal_observation) where the episode was truncated
@@ -177,7 +234,7 @@ class PPO:
             # terminal_observation rows of envs that never finished are zeros, so the masked product is finite)
             if hasattr(infos, "truncated"):
                 with torch.no_grad():
-                    tv = self.policy.value(infos.terminal_observation)
+                    tv = self.policy.value_fused(infos.terminal_observation, params) if fused else self.policy.value(infos.terminal_observation)
                 rew = rew + cfg.gamma * tv * infos.truncated.to(rew.dtype)
             b["rewards"][t].copy_(rew)
             b["dones"][t].copy_(done_f)
@@ -188,7 +245,7 @@ class PPO:
                 ep_cnt += d64.sum()
             self._obs = obs.clone()
         with torch.no_grad():
-            last_values = self.policy.value(self._obs)
+            last_values = self.policy.value_fused(self._obs, params) if fused else self.policy.value(self._obs)
         adv, ret = compute_gae(b["rewards"], b["values"], b["dones"], last_values, cfg.gamma, cfg.gae_lambda)
         b["adv"], b["ret"] = adv, ret
         self.num_timesteps += cfg.n_steps * env.num_envs * self.world
@@ -198,7 +255,55 @@ class PPO:
         return {"ep_rew_mean": r / c if c else float("nan"), "ep_len_mean": l / c if c else float("nan"), "episodes": c}
 
     # ---- update
+    def _train_fused(self) -> Dict[str, float]:
+        """train() with forward + loss + backward of a minibatch as two CUDA launches (csrc/brb_policy.cu: brb_ppo_grad, one
+        per tower) instead of the autograd graph; Adam, gradient clipping and the all-reduce stay in PyTorch."""
+        import ctypes as C
+        from . import _cabi
+        cfg, b, pol = self.cfg, self.buf, self.policy
+        T, n = b["rewards"].shape
+        total = T * n
+        mb = total // cfg.n_minibatches
+        obs, act = b["obs"].reshape(total, 6), b["actions"].reshape(total, 2)
+        oldlp, adv, ret = b["logp"].reshape(total), b["adv"].reshape(total).contiguous(), b["ret"].reshape(total).contiguous()
+        if getattr(self, "_gflat", None) is None:
+            self._gflat = torch.zeros(_cabi.POLICY_NPARAM, device=self.device)
+            self._gstats = torch.zeros(4, device=self.device)
+            off = 0
+            for p in pol.packed_parameters():            # every .grad is a view of the flat gradient the kernel fills
+                p.grad = self._gflat[off:off + p.numel()].view_as(p)
+                off += p.numel()
+        L, stream = _cabi.lib(), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+        logs = torch.zeros(4, device=self.device)
+        unit = torch.tensor([0.0, 1.0], device=self.device)
+        updates = 0
+        for _ in range(cfg.n_epochs):
+            perm = torch.randperm(total, device=self.device, generator=self.gen)
+            for k in range(cfg.n_minibatches):
+                idx = perm[k * mb:(k + 1) * mb]
+                if cfg.normalize_advantage and mb > 1:
+                    a = adv[idx]
+                    astats = torch.stack([a.mean(), 1.0 / (a.std() + 1e-8)])
+                else:
+                    astats = unit
+                params = pol.pack_params()
+                self._gflat.zero_(); self._gstats.zero_()
+                with torch.cuda.device(self.device):
+                    _cabi.check(L.brb_ppo_grad(params.data_ptr(), obs.data_ptr(), act.data_ptr(), oldlp.data_ptr(), adv.data_ptr(),
+                                               ret.data_ptr(), idx.data_ptr(), mb, astats.data_ptr(), cfg.clip_range, cfg.vf_coef,
+                                               cfg.ent_coef, self._gflat.data_ptr(), self._gstats.data_ptr(), stream), "brb_ppo_grad")
+                if self.world > 1:
+                    self._all_reduce_(self._gflat).div_(self.world)
+                torch.nn.utils.clip_grad_norm_(pol.parameters(), cfg.max_grad_norm)
+                self.optimizer.step()
+                logs += self._gstats
+                updates += 1
+        vals = (logs / max(1, updates)).tolist()
+        return dict(zip(("policy_loss", "value_loss", "approx_kl", "clip_fraction"), vals))
+
     def train(self) -> Dict[str, float]:
+        if self.fused_update and self.device.type == "cuda" and self.policy.action_net.in_features == 64:
+            return self._train_fused()
         cfg, b = self.cfg, self.buf
         T, n = b["rewards"].shape
         flat = {k: v.reshape(T * n, *v.shape[2:]) for k, v in b.items()}

@@ -127,6 +127,30 @@ int64_t brb_env_num_launches(const BrbEnv *e);
 /* FP32-pipe peak probe: runs an FFMA-bound kernel and returns achieved FLOP/s (for the roofline denominator). */
 int brb_fp32_peak_flops(int device, double *flops_out, double *ms_out);
 
+/* PPO actor-critic forward for the rollout: policy.forward(obs) of SB3's ActorCriticPolicy("MlpPolicy") as the reference
+ * configures it (src/sb_rl.py:63-71: pi = vf = [64, 64], tanh, state-independent log_std), one launch for n robots.
+ * params: BRB_POLICY_NPARAM fp32 on the device in SB3 state-dict order
+ *   mlp_extractor.policy_net.{0,2}.{weight,bias}, mlp_extractor.value_net.{0,2}.{weight,bias},
+ *   action_net.{weight,bias}, value_net.{weight,bias}, log_std.
+ * obs [n,6]; noise [n,2] standard normal draws (NULL = deterministic: actions = mean).  Outputs: actions [n,2] (the
+ * unclipped sample the rollout buffer keeps), actions_clipped [n,2] (what the env receives; may be NULL), values [n],
+ * log_prob [n] of the unclipped action.  actions == NULL: critic only (values of the given observations, e.g. V(terminal
+ * observation) for the TimeLimit bootstrap).  All pointers are device pointers. */
+#define BRB_POLICY_NPARAM 9413
+int brb_policy_act(const float *params, const float *obs, const float *noise, int64_t n, float *actions, float *actions_clipped,
+                   float *values, float *logp, void *stream);
+
+/* One PPO minibatch, forward + loss + backward fused (SB3 PPO.train() inner loop, third party; reference src/sb_rl.py:63-71
+ * runs it with SB3's defaults): for the mb samples idx[0..mb) of the rollout buffer (obs [S,6], actions [S,2] unclipped,
+ * old_logp / adv / returns [S])
+ *   loss = -mean(min(A r, A clamp(r, 1 - clip, 1 + clip))) + vf_coef mean((returns - V)^2) - ent_coef mean(entropy),
+ *   r = exp(log_prob - old_logp), A = (adv - adv_stats[0]) * adv_stats[1]   (per-minibatch normalisation: mean, 1 / (std + eps))
+ * grad [BRB_POLICY_NPARAM] (parameter-block layout) and stats[4] = {policy_loss, value_loss, approx_kl, clip_fraction}
+ * are ACCUMULATED: zero them before the call.  All pointers are device pointers. */
+int brb_ppo_grad(const float *params, const float *obs, const float *actions, const float *old_logp, const float *adv, const float *returns,
+                 const int64_t *idx, int64_t mb, const float *adv_stats, float clip_range, float vf_coef, float ent_coef, float *grad,
+                 float *stats, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -55,3 +55,93 @@ def test_policy_rollout_throughput_path_runs():
         obs, r, d, info = env.step(a.clamp(-1, 1))
     assert torch.isfinite(obs).all() and torch.isfinite(r).all()
     env.close()
+
+
+def test_fused_policy_forward_matches_the_torch_policy():
+    """brb_policy_act (one launch: both towers, sample, log-prob, value, clipped action) against the plain PyTorch fp32
+    MlpPolicy.act on the same weights, observations and noise draws."""
+    from balance_robot_b200.ppo import MlpPolicy
+    torch.manual_seed(3)
+    pol = MlpPolicy().cuda()
+    with torch.no_grad():                                   # move the weights off their orthogonal init
+        for p in pol.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+        pol.log_std.copy_(torch.tensor([-0.3, 0.2]))
+    n = 100_003                                             # not a multiple of the CTA size, several grid-stride passes
+    obs = torch.randn((n, 6), device="cuda") * torch.tensor([1.5, 3.0, 1.0, 1.0, 1.0, 1.0], device="cuda")
+    g1 = torch.Generator(device="cuda").manual_seed(11)
+    g2 = torch.Generator(device="cuda").manual_seed(11)
+    a_ref, v_ref, lp_ref = pol.act(obs, generator=g1)
+    a, v, lp, ac = pol.act_fused(obs, generator=g2)
+    assert (a - a_ref).abs().max() < 1e-5 and (v - v_ref).abs().max() < 1e-5
+    assert (lp - lp_ref).abs().max() < 1e-4                 # log-prob has a 1 / (2 var) ~ 1 gain on (a - mean)^2 up to ~10
+    assert torch.equal(ac, a.clamp(-1.0, 1.0))
+    assert (pol.value_fused(obs) - v_ref).abs().max() < 1e-5
+    a_det, _, lp_det, _ = pol.act_fused(obs, deterministic=True)
+    a_det_ref, _, lp_det_ref = pol.act(obs, deterministic=True)
+    assert (a_det - a_det_ref).abs().max() < 1e-5 and (lp_det - lp_det_ref).abs().max() < 1e-5
+    # throughput of the fused call at BASELINE configs[2] size (reported, with a loose floor)
+    big = torch.randn((1 << 20, 6), device="cuda")
+    params = pol.pack_params()
+    for _ in range(3):
+        pol.act_fused(big, generator=g2, params=params)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(10):
+        pol.act_fused(big, generator=g2, params=params)
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 10
+    print(f"fused policy forward, 1M robots: {ms:.3f} ms ({(1 << 20) / ms * 1e3:.3e} robots/s)")
+    assert ms < 3.0
+
+
+def test_fused_ppo_gradient_matches_autograd():
+    """brb_ppo_grad (forward + clipped-surrogate / value loss + backward, two launches) against PyTorch autograd on the same
+    minibatch: gradient of every parameter and the four logged statistics."""
+    import ctypes as C
+    from balance_robot_b200 import _cabi
+    env = make_vec("Env01-v1", 4096, seed=2)
+    cfg = PPOConfig(n_steps=8, seed=2, ent_coef=0.01)
+    agent = PPO(env, cfg, device="cuda:0")
+    agent.collect_rollouts()
+    pol, b = agent.policy, agent.buf
+    torch.manual_seed(5)
+    with torch.no_grad():                                    # move away from the rollout policy: ratios != 1, some get clipped
+        for p in pol.parameters():
+            p.add_(0.03 * torch.randn_like(p))
+    total = 8 * 4096
+    flat = {k: v.reshape(total, *v.shape[2:]) for k, v in b.items()}
+    mb = 10_001                                              # not a multiple of the 128-sample tiles
+    idx = torch.randperm(total, device="cuda")[:mb].contiguous()
+    adv = flat["adv"][idx]
+    astats = torch.stack([adv.mean(), 1.0 / (adv.std() + 1e-8)])
+    advn = (adv - astats[0]) * astats[1]
+    values, logp, entropy = pol.evaluate_actions(flat["obs"][idx], flat["actions"][idx])
+    ratio = torch.exp(logp - flat["logp"][idx])
+    pl = -torch.min(advn * ratio, advn * torch.clamp(ratio, 1 - cfg.clip_range, 1 + cfg.clip_range)).mean()
+    vl = torch.nn.functional.mse_loss(flat["ret"][idx], values)
+    loss = pl + cfg.vf_coef * vl - cfg.ent_coef * entropy.mean()
+    pol.zero_grad()
+    loss.backward()
+    g_ref = torch.cat([p.grad.reshape(-1) for p in pol.packed_parameters()])
+    lr = (logp - flat["logp"][idx]).detach()
+    s_ref = torch.stack([pl.detach(), vl.detach(), ((torch.exp(lr) - 1) - lr).mean(), ((ratio.detach() - 1).abs() > cfg.clip_range).float().mean()])
+    assert float(s_ref[3]) > 0.01                            # the clipped branch is exercised
+
+    g = torch.zeros(_cabi.POLICY_NPARAM, device="cuda"); st = torch.zeros(4, device="cuda")
+    params = pol.pack_params()
+    _cabi.check(_cabi.lib().brb_ppo_grad(params.data_ptr(), flat["obs"].data_ptr(), flat["actions"].data_ptr(), flat["logp"].data_ptr(),
+                                         flat["adv"].contiguous().data_ptr(), flat["ret"].contiguous().data_ptr(), idx.data_ptr(), mb,
+                                         astats.data_ptr(), cfg.clip_range, cfg.vf_coef, cfg.ent_coef, g.data_ptr(), st.data_ptr(),
+                                         C.c_void_p(torch.cuda.current_stream().cuda_stream)), "brb_ppo_grad")
+    torch.cuda.synchronize()
+    err = (g - g_ref).abs().max() / g_ref.abs().max()
+    assert err < 2e-4, float(err)
+    off = 0
+    for p in pol.packed_parameters():                        # and block by block, relative to each block's own scale
+        k = p.numel()
+        e = (g[off:off + k] - g_ref[off:off + k]).abs().max() / (g_ref[off:off + k].abs().max() + 1e-12)
+        assert e < 1e-3, (off, float(e))
+        off += k
+    assert torch.allclose(st, s_ref, rtol=1e-3, atol=1e-6), (st, s_ref)
+    env.close()
