@@ -35,8 +35,8 @@ ALG_FLOP_PER_ENV_STEP = FLOP_PER_SUBSTEP_CONTACT * FRAME_SKIP          # 9.25e5 
 ALG_BYTES_PER_ENV_STEP = 290.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum of brb_step_kernel<1> from the committed `ncu --set full` capture
-# (profiles/r1_step_kernel_ncu_raw.csv: 13,971,968 + 5,376 bytes for 65,536 robots) -> bytes per robot-step
-NCU_DRAM_BYTES_PER_ENV_STEP = (13971968 + 5376) / 65536
+# (profiles/r1_step_kernel_ncu_raw.csv: 13,970,688 + 7,168 bytes for 65,536 robots) -> bytes per robot-step
+NCU_DRAM_BYTES_PER_ENV_STEP = (13970688 + 7168) / 65536
 
 
 def parse_args():
@@ -181,11 +181,12 @@ def run_b200(args, rank, world, local_rank):
     _cabi.check(_cabi.lib().brb_fp32_peak_flops(local_rank, C.byref(fl), C.byref(ms)), "brb_fp32_peak_flops")
     fp32_peak = fl.value
 
-    policy = None
+    policy = policy_params = None
     if args.actions == "policy":
         from balance_robot_b200.ppo import MlpPolicy
         torch.manual_seed(0)
         policy = MlpPolicy().to(dev)
+        policy_params = policy.pack_params()
     obs_t = env.reset()
 
     def one_step(k):
@@ -193,8 +194,8 @@ def run_b200(args, rank, world, local_rank):
         if policy is None:
             obs_t = env.step(acts[k % nact])[0]
         else:
-            a, _, _ = policy.act(obs_t, generator=gen)
-            obs_t = env.step(a.clamp(-1.0, 1.0))[0]
+            _, _, _, a = policy.act_fused(obs_t, generator=gen, params=policy_params)      # one launch (csrc/brb_policy.cu)
+            obs_t = env.step(a)[0]
 
     for k in range(args.spinup + args.warmup):
         one_step(k)
