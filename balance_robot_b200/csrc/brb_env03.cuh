@@ -58,7 +58,7 @@ BRB_D void blk_setup(const BrbModelConsts &c, Blk &B) {
     const float px = B.v[0] + wwy * rz - wwz * cy, py = B.v[1] + wwz * cx - wwx * rz, pz = B.v[2] + wwx * cy - wwy * cx;
     const float imp = imp_of(pp, dist);
     B.cr[k][0] = cx; B.cr[k][1] = cy; B.cr[k][2] = rz;
-    B.cD[k] = pp[3] * imp / (1.f - imp);
+    B.cD[k] = __fdividef(pp[3] * imp, 1.f - imp);
     B.cy[k][0] = pp[2] * pz + pp[1] * imp * (dist - pp[7]);
     B.cy[k][1] = pp[2] * py;
     B.cy[k][2] = -pp[2] * px;
@@ -514,7 +514,7 @@ BRB_D void cb_setup(const BrbModelConsts &c, const Phys &P, const Blk &B, const 
                          (B.v[1] + wb[2] * rb[0] - wb[0] * rb[2]) - (P.v[1].s + wr[2] * ra[0] - wr[0] * ra[2]),
                          (B.v[2] + wb[0] * rb[1] - wb[1] * rb[0]) - (P.v[2].s + wr[0] * ra[1] - wr[1] * ra[0])};
     const float imp = imp_of(pp, bdist[k2]);
-    Q.D[n] = pp[3] * imp / (1.f - imp);
+    Q.D[n] = __fdividef(pp[3] * imp, 1.f - imp);
     for (int k = 0; k < 3; k++) { Q.n[n][k] = nn[k]; Q.t1[n][k] = t1[k]; Q.t2[n][k] = t2[k]; Q.ra[n][k] = ra[k]; Q.rb[n][k] = rb[k]; }
     Q.y[n][0] = pp[2] * dot3f(nn, dv) + pp[1] * imp * (bdist[k2] - pp[7]);
     Q.y[n][1] = pp[2] * dot3f(t1, dv);

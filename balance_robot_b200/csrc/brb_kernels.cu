@@ -226,7 +226,7 @@ BRB_D void phys_world_force(const BrbModelConsts &c, const Phys &P, float (&r)[8
 // ---- A.3 steps 2-7: kinematics, smooth forces, collision, reference accelerations
 // impedance imp(dist) of a dynamic pair (solimp midpoint 0.5, power 2).  pp = {mu, K, B, D1, d0, d1, width, margin}
 BRB_D float imp_of(const float *pp, float dist) {
-  const float x = fabsf(dist - pp[7]) / pp[6];
+  const float x = __fdividef(fabsf(dist - pp[7]), pp[6]);
   if (x >= 1.f) return pp[5];
   const float y = (x <= 0.5f) ? 2.f * x * x : 1.f - 2.f * (1.f - x) * (1.f - x);
   return pp[4] + y * (pp[5] - pp[4]);
@@ -254,7 +254,7 @@ BRB_D void contact_setup(const BrbModelConsts &c, Phys &P, float d0, float anx, 
     P.cw[CI][0] = wx; P.cw[CI][1] = wy; P.cw[CI][2] = wz;
     if (VI) {
       const float imp = imp_of(c.pp[0], dist);
-      P.cD[CI] = c.pp[0][3] * imp / (1.f - imp);
+      P.cD[CI] = __fdividef(c.pp[0][3] * imp, 1.f - imp);
       P.cy[CI][0] = c.pp[0][2] * pz + c.pp[0][1] * imp * dist;
       P.cy[CI][1] = c.pp[0][2] * py;
       P.cy[CI][2] = -c.pp[0][2] * px;
