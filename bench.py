@@ -102,7 +102,7 @@ def run_reference(args, rank, world):
     threads = args.cpu_threads or (os.cpu_count() or 1)
     value, dt, n = cpu_leg(args, args.steps, args.warmup, threads)
     sample = f"{n} envs (64 per thread) x {args.steps} steps after {args.spinup} spin-up + {args.warmup} warm-up, same action distribution, replayed Philox draws"
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC.replace(ENV_ID, args.env), "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic", "config": workload_config(args, world), "impl": "reference",
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
@@ -300,7 +300,7 @@ def run_b200(args, rank, world, local_rank):
         v, dt, ncpu = cpu_leg(args, 120, 10, threads)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"{ncpu} envs (64 per thread) x 120 steps after {args.spinup} spin-up + 10 warm-up ({dt:.1f} s timed), fp64 oracle, replayed Philox draws"}
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+    line = {"metric": METRIC.replace(ENV_ID, args.env), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu_baseline,
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "wall_s": wall,
