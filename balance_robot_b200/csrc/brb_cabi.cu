@@ -96,7 +96,7 @@ extern "C" void brb_model_destroy(BrbModel *m) {
 static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64_t env_id_offset, BrbEnv **out) {
-  if (!m || !out || n <= 0) return BRB_EINVAL;
+  if (!m || !out || n <= 0 || n > 0x7FFFFFFFLL) return BRB_EINVAL;      // the visit order holds 32-bit env indices
   CK(cudaSetDevice(m->device));
   BrbEnv *e = (BrbEnv *)calloc(1, sizeof(BrbEnv));
   if (!e) return BRB_ENOMEM;
