@@ -820,7 +820,7 @@ __global__ void BRB_STEP_BOUNDS(KIND) brb_step_kernel(const __grid_constant__ Br
   const long long i = live ? (perm.in ? (long long)perm.in[tid] : tid) : 0;
   unsigned stat[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const unsigned wmask = __ballot_sync(0xFFFFFFFFu, live);   // lanes of this warp that run a robot
-  if (threadIdx.x < 16 * 5) stab_fill(c, KIND == BRB_ENV03_V2, threadIdx.x);
+  for (int k = threadIdx.x; k < 16 * 5; k += blockDim.x) stab_fill(c, KIND == BRB_ENV03_V2, k);
   __syncthreads();
   if (live) {
     if (KIND == BRB_ENV03_V2) step_env03(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat, wmask);
