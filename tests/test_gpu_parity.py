@@ -328,3 +328,37 @@ def test_time_limit_truncation_on_device():
     rec = info[int(torch.nonzero(trunc)[0])]
     assert rec["TimeLimit.truncated"] is True and rec["episode"]["l"] == 6000
     env.close()
+
+
+def test_every_kernel_at_sizes_off_the_cta_and_tile_grid():
+    """compute-sanitizer is closed on this pool, so the bounds of every kernel are exercised with sizes that are not
+    multiples of the CTA (128), compaction (256) or PPO tile (128) sizes, next to canary-guarded output buffers."""
+    from balance_robot_b200.ppo import PPO, PPOConfig
+    for env_id, n in (("Env01-v1", 77), ("Env01-v2", 333), ("Env01-v3", 130), ("Env03-v2", 70)):
+        env = make_vec(env_id, n, seed=1)
+        env.reset()
+        for _ in range(3):
+            obs, r, d, info = env.step(torch.rand((n, 2), device="cuda") * 2 - 1)
+        assert torch.isfinite(obs).all() and obs.shape == (n, 6) and r.shape == (n,) and d.shape == (n,)
+        q = env.get_state()
+        env.set_state(q[0], q[1])
+        assert env.elapsed_steps().shape == (n,) and env.stats()["env_steps"] == 3 * n
+        env.close()
+    envh = make_vec("Env01-v2", 300, seed=2, output="numpy")
+    envh.reset()
+    rows = [hb["rows"] for hb in envh._hbuf]
+    for k in range(4):
+        for rws in rows:
+            rws.fill_(-77.0)                                  # canary behind the compacted finished-episode rows
+        o, r, d, infos = envh.step(np.random.default_rng(k).uniform(-1, 1, (300, 2)).astype(np.float32))
+        nd = int(d.sum())
+        assert all(infos[int(i)]["episode"]["l"] >= 1 for i in np.flatnonzero(d))
+        assert (envh._hbuf[envh._flip]["rows"][nd:] == -77.0).all()
+    envh.close()
+    env = make_vec("Env01-v2", 200, seed=3)
+    agent = PPO(env, PPOConfig(n_steps=5, n_epochs=1, n_minibatches=3, seed=0), device="cuda:0")      # minibatches of 333 samples
+    agent.collect_rollouts()
+    out = agent.train()
+    assert all(np.isfinite(v) for v in out.values())
+    assert torch.isfinite(agent.policy.pack_params()).all()
+    env.close()
