@@ -657,7 +657,7 @@ BRB_D int env03_detect(const BrbModelConsts &c, const Phys &P, const Blk &B, flo
 // decouples exactly).  A single code path keeps the loop body inside the instruction cache: the first version had
 // separate robot / block / coupled solvers and was fetch-bound (ncu: stall_no_instruction 4.9 per issue, profiles/).
 template <int MAXIT>
-BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&qstale)[4], float (&pstale)[3], Env03Stats &es, const unsigned wmask) {
+BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&qstale)[4], float (&pstale)[3], Env03Stats &es, const unsigned wmask, const bool ctasync) {
   int sidx = 0, it = 0, nbb = 0, qprev_nc = -1;
   bool need_setup = true, done = false;   // warp-uniform loop + explicit reconvergence: see phys_run
   float bpos[8][3], bdist[8], bn[3];
@@ -666,13 +666,16 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
   unsigned was = 0u;
   int wasn = -1;
   for (;;) {
-    if (!__any_sync(wmask, !done)) break;
+    if (!(ctasync ? BRB_CTA_OR(!done) : __any_sync(wmask, !done))) break;
     if (!done && need_setup) {
       phys_setup<true>(c, P);
       const unsigned fresh = P.valid & ~was;
       P.bits |= ((fresh & 1u) ? 0xFu : 0u) | ((fresh & 2u) ? 0xF0u : 0u) | ((fresh & 4u) ? 0xF00u : 0u) | ((fresh & 8u) ? 0xF000u : 0u);
       blk_setup(c, B);
       if (B.nc != wasn) B.bits = 0xFFFFu;
+    }
+    if (ctasync) BRB_CTA_SYNC();
+    if (!done && need_setup) {
       nbb = env03_detect(c, P, B, bpos, bdist, bn);
       Q.nc = 0;
       if (nbb > 0) {
@@ -698,7 +701,7 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
       }
     }
 #endif
-    __syncwarp(wmask);
+    if (ctasync) BRB_CTA_SYNC(); else __syncwarp(wmask);
     if (done) {
     } else if (P.valid || B.nc > 0 || Q.nc > 0) {
       coupled_solve_fast(c, P, B, Q, ar, ab);
@@ -740,7 +743,7 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
       ar[7] = c.minv_blk[3] * f[1] + c.minv_blk[6] * f[3] + c.minv_blk[8] * f[6] + c.minv_blk[9] * f[7];
       ab[0] = 0.f; ab[1] = 0.f; ab[2] = -c.grav; ab[3] = 0.f; ab[4] = 0.f; ab[5] = 0.f;
     }
-    __syncwarp(wmask);
+    if (ctasync) BRB_CTA_SYNC(); else __syncwarp(wmask);
     if (!done && conv) {
       if (sidx == nsub - 1) {
 #pragma unroll
@@ -829,7 +832,7 @@ BRB_D void reset_env03(const BrbState &S, long long i, const double *u, float o[
 BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long long i, const float *__restrict__ actions,
                       float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done,
                       uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs, float *__restrict__ ep_return_out,
-                      int32_t *__restrict__ ep_len_out, const double *__restrict__ replay_u, unsigned stat[12], const unsigned wmask) {
+                      int32_t *__restrict__ ep_len_out, const double *__restrict__ replay_u, unsigned stat[12], const unsigned wmask, const bool ctasync) {
   const long long N = S.n;
   double qvel[14], xq[4];
   for (int k = 0; k < 14; k++) qvel[k] = S.qvel[k * N + i];
@@ -868,7 +871,7 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
   KF qprev[4];
   float pstale[3];
   Env03Stats es = {0u, 0u, 0u, 0u, 0u, 0u};
-  phys03_run<BRB_MAXIT>(c, st, B, c.frame_skip, qprev, pstale, es, wmask);
+  phys03_run<BRB_MAXIT>(c, st, B, c.frame_skip, qprev, pstale, es, wmask, ctasync);
   stat[0] = c.frame_skip; stat[1] = st.n_contact; stat[2] = st.n_solve; stat[3] = st.n_nonconv; stat[7] = st.n_slots;
   stat[8] = es.coupled; stat[9] = es.blk_contact; stat[10] = es.fallback; stat[11] = es.csolves;
   {

@@ -12,4 +12,6 @@ static inline float __fdividef(float a, float b) { return a / b; }
 // one robot per call on the host: the warp-level votes of the per-lane state machine degenerate
 #define __any_sync(mask, pred) (pred)
 #define __syncwarp(mask) ((void)0)
+#define BRB_CTA_OR(p) (p)
+#define BRB_CTA_SYNC() ((void)0)
 #endif
