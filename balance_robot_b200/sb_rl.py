@@ -137,7 +137,46 @@ def _out_of_scope(name, why):
     return _cmd
 
 
-_out_of_scope("test", "interactive MuJoCo viewer roll-out (sb_rl.py:136-182)")
+@cli.command(help="Test the current model (headless: the reference opens the MuJoCo viewer, sb_rl.py:136-182)")
+@click.option("-e", "--environment", required=True, type=str, help="id of the environment (eg; Env01-v1)")
+@click.option("--show-io", is_flag=True, default=False, help="log model inputs and outputs")
+@click.option("--show-i", is_flag=True, default=False, help="log model inputs to std out in Python array syntax")
+@click.option("--episodes", default=20, show_default=True, type=int, help="episodes to run (the reference loops until interrupted)")
+@click.option("--device", default="cuda:0", type=str)
+@click.pass_context
+def test(ctx, environment, show_io, show_i, episodes, device):
+    algo, model_file = ctx.obj["algorithm"], ctx.obj["model_file"]
+    spec = registry.spec(environment)
+    if model_file is None:                                                                          # default name, sb_rl.py:147-149
+        model_file = os.path.join(MODEL_DIR, f"{environment}_{algo}", "best_model.zip")
+    if not os.path.isfile(model_file):
+        raise RuntimeError(f"Could not open model file: {model_file}")                              # sb_rl.py:151-152
+    logging.info("Starting test simulation")
+    logging.info("Algorithm: %s", algo)
+    logging.info("Environment: %s", environment)
+    logging.info("Model: %s", model_file)
+    n = max(1, min(episodes, 64))
+    env = make_vec(environment, n, device=device, seed=12345)
+    agent = PPO.load(model_file, env, PPOConfig(), device=device)
+    obs = env.reset()
+    returns, lengths, k = [], [], 0
+    while len(returns) < episodes and k < 4 * spec.max_episode_steps:
+        action, _ = agent.policy.predict(obs)                                                       # model.predict(obs), sb_rl.py:166
+        if (show_io or show_i) and k % 30 == 0:
+            row = [float(v) for v in obs[0].tolist()] + ([float(v) for v in action[0].tolist()] if show_io else [])
+            logging.info(str(row) + ("," if show_i and not show_io else ""))
+        obs, _, done, infos = env.step(action)
+        for i in torch.nonzero(done).flatten().tolist():
+            returns.append(float(infos.episode_return[i])); lengths.append(int(infos.episode_length[i]))
+        k += 1
+    returns, lengths = returns[:episodes], lengths[:episodes]
+    if returns:
+        logging.info("episodes %d  mean return %.2f  mean length %.1f  (min %d, max %d)", len(returns), sum(returns) / len(returns),
+                     sum(lengths) / len(lengths), min(lengths), max(lengths))
+        click.echo(f"episodes={len(returns)} mean_return={sum(returns) / len(returns):.3f} mean_length={sum(lengths) / len(lengths):.1f}")
+    env.close()
+
+
 _out_of_scope("convert", "ONNX export (sb_rl.py:86-133)")
 _out_of_scope("test-onnx", "onnxruntime roll-out (sb_rl.py:185-247)")
 _out_of_scope("test-tflite", "TFLite roll-out (sb_rl.py:250-306)")

@@ -37,6 +37,10 @@ def test_cli_train_writes_reference_style_artifacts(tmp_path):
     assert (run / "best_model.zip").exists()                                   # EvalCallback target, sb_rl.py:542
     assert list(run.glob("Env01-v2_PPO_cp__*_steps.zip"))                      # CheckpointCallback naming, sb_rl.py:545-550
     assert (tmp_path / "logs").is_dir() and (tmp_path / "movies").is_dir()
+    # `test` with the default model name (sb_rl.py:147-149), headless here
+    res_t = subprocess.run([sys.executable, str(ROOT / "sb_rl.py"), "-a", "PPO", "test", "-e", "Env01-v2", "--episodes", "6", "--show-io"],
+                           cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert res_t.returncode == 0 and "episodes=6 mean_return=" in res_t.stdout, res_t.stderr[-2000:]
     # fine-tune from the saved model with -m on Env03-v2, as README.md:62 does (BASELINE.json configs[3])
     cmd2 = [sys.executable, str(ROOT / "sb_rl.py"), "-a", "PPO", "-m", str(run / "best_model.zip"), "train", "-e", "Env03-v2",
             "--num-envs", "512", "--total-timesteps", "20000", "--n-steps", "16"]

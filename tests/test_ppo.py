@@ -135,7 +135,9 @@ def test_cli_surface():
     assert r.invoke(cli, ["train", "-e", "Env01-v2"]).exit_code != 0                      # -a is required, as in the reference
     assert "not a Stable Baselines3 algorithm" in r.invoke(cli, ["-a", "XYZ", "train", "-e", "Env01-v2"]).output
     assert "only PPO" in r.invoke(cli, ["-a", "SAC", "train", "-e", "Env01-v2"]).output
-    assert "outside the B200 hot-path scope" in r.invoke(cli, ["-a", "PPO", "test", "-e", "Env01-v2"]).output
+    assert "outside the B200 hot-path scope" in r.invoke(cli, ["-a", "PPO", "convert", "-e", "Env01-v2"]).output
+    res = r.invoke(cli, ["-a", "PPO", "test", "-e", "Env01-v2"])                          # default model name, missing here (sb_rl.py:147-152)
+    assert isinstance(res.exception, RuntimeError) and "Could not open model file" in str(res.exception)
     out = r.invoke(cli, ["-a", "PPO", "train", "--help"]).output
     assert "--environment" in out and "--num-envs" in out
 
