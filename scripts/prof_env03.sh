@@ -5,4 +5,3 @@ ncu --set full --clock-control none --import-source on -k regex:brb_step -s 44 -
 ncu -i gpurun_out/prof_e3.ncu-rep --page raw --csv > gpurun_out/raw_e3.csv 2>/dev/null
 ncu -i gpurun_out/prof_e3.ncu-rep --page source --csv > gpurun_out/src_e3.csv 2>/dev/null
 tail -1 gpurun_out/plain_e3.log | cut -c1-300
-python scripts/tripstats.py Env03-v2 | head -3
