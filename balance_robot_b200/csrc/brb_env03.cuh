@@ -491,7 +491,8 @@ BRB_D int env03_coupled_substep(const BrbModelConsts &c, const Phys &P, const Bl
 // Chassis-block contacts of the current substep (general contact frame).  Indexed at run time -> local memory; the
 // accumulators they feed (H, Hb, Cc) are indexed at compile time and stay in registers.
 struct CBSet {
-  float n[8][3], t1[8][3], t2[8][3], ra[8][3], rb[8][3], y[8][3], D[8];
+  float n[3], t1[3], t2[3];          // one contact frame for the whole box-box manifold (registers)
+  float ra[8][3], rb[8][3], y[8][3], D[8];   // per contact (run-time index: local memory)
   int nc;
   unsigned bits;   // 4 pyramid rows per contact
 };
@@ -505,6 +506,7 @@ BRB_D void cb_setup(const BrbModelConsts &c, const Phys &P, const Blk &B, const 
                        B.ex[2] * B.w[0] + B.ey[2] * B.w[1] + B.ez[2] * B.w[2]};
   float nn[3] = {bn[0], bn[1], bn[2]}, t1[3], t2[3];
   make_frame3(nn, t1, t2);
+  for (int k = 0; k < 3; k++) { Q.n[k] = nn[k]; Q.t1[k] = t1[k]; Q.t2[k] = t2[k]; }
   int n = 0;
   for (int k2 = 0; k2 < nbb && n < 8; k2++) {
     if (bdist[k2] >= pp[7]) continue;
@@ -515,7 +517,7 @@ BRB_D void cb_setup(const BrbModelConsts &c, const Phys &P, const Blk &B, const 
                          (B.v[2] + wb[0] * rb[1] - wb[1] * rb[0]) - (P.v[2].s + wr[0] * ra[1] - wr[1] * ra[0])};
     const float imp = imp_of(pp, bdist[k2]);
     Q.D[n] = __fdividef(pp[3] * imp, 1.f - imp);
-    for (int k = 0; k < 3; k++) { Q.n[n][k] = nn[k]; Q.t1[n][k] = t1[k]; Q.t2[n][k] = t2[k]; Q.ra[n][k] = ra[k]; Q.rb[n][k] = rb[k]; }
+    for (int k = 0; k < 3; k++) { Q.ra[n][k] = ra[k]; Q.rb[n][k] = rb[k]; }
     Q.y[n][0] = pp[2] * dot3f(nn, dv) + pp[1] * imp * (bdist[k2] - pp[7]);
     Q.y[n][1] = pp[2] * dot3f(t1, dv);
     Q.y[n][2] = pp[2] * dot3f(t2, dv);
@@ -532,9 +534,9 @@ BRB_D unsigned cb_active_set(const BrbModelConsts &c, const CBSet &Q, const floa
     const float dx = (ab[0] + ab[4] * rb[2] - ab[5] * rb[1]) - (ar[0] + ar[4] * ra[2] - ar[5] * ra[1]);
     const float dy = (ab[1] + ab[5] * rb[0] - ab[3] * rb[2]) - (ar[1] + ar[5] * ra[0] - ar[3] * ra[2]);
     const float dz = (ab[2] + ab[3] * rb[1] - ab[4] * rb[0]) - (ar[2] + ar[3] * ra[1] - ar[4] * ra[0]);
-    const float z0 = Q.n[k][0] * dx + Q.n[k][1] * dy + Q.n[k][2] * dz + Q.y[k][0];
-    const float z1 = mu * (Q.t1[k][0] * dx + Q.t1[k][1] * dy + Q.t1[k][2] * dz + Q.y[k][1]);
-    const float z2 = mu * (Q.t2[k][0] * dx + Q.t2[k][1] * dy + Q.t2[k][2] * dz + Q.y[k][2]);
+    const float z0 = Q.n[0] * dx + Q.n[1] * dy + Q.n[2] * dz + Q.y[k][0];
+    const float z1 = mu * (Q.t1[0] * dx + Q.t1[1] * dy + Q.t1[2] * dz + Q.y[k][1]);
+    const float z2 = mu * (Q.t2[0] * dx + Q.t2[1] * dy + Q.t2[2] * dz + Q.y[k][2]);
     const unsigned pb = prev >> (4 * k);
     const float e0 = (pb & 1u) ? eps : -eps, e1 = (pb & 2u) ? eps : -eps, e2 = (pb & 4u) ? eps : -eps, e3 = (pb & 8u) ? eps : -eps;
     bits |= ((unsigned)(z0 + z1 < e0) | ((unsigned)(z0 - z1 < e1) << 1) | ((unsigned)(z0 + z2 < e2) << 2) | ((unsigned)(z0 - z2 < e3) << 3)) << (4 * k);
@@ -560,7 +562,7 @@ BRB_D void coupled_solve_fast(const BrbModelConsts &c, const Phys &P, const Blk 
     const float b0 = (float)(b & 1u), b1 = (float)((b >> 1) & 1u), b2 = (float)((b >> 2) & 1u), b3 = (float)((b >> 3) & 1u);
     const float Dc = Q.D[k], Dm = Dc * mu, Dmm = Dm * mu;
     const float W00 = Dc * (b0 + b1 + b2 + b3), W01 = Dm * (b0 - b1), W02 = Dm * (b2 - b3), W11 = Dmm * (b0 + b1), W22 = Dmm * (b2 + b3);
-    const float *n = Q.n[k], *t1 = Q.t1[k], *t2 = Q.t2[k];
+    const float *n = Q.n, *t1 = Q.t1, *t2 = Q.t2;
     float g0[3], g1[3], g2[3], S[3][3];
 #pragma unroll
     for (int j = 0; j < 3; j++) { g0[j] = W00 * n[j] + W01 * t1[j] + W02 * t2[j]; g1[j] = W01 * n[j] + W11 * t1[j]; g2[j] = W02 * n[j] + W22 * t2[j]; }
