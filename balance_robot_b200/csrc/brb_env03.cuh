@@ -65,9 +65,9 @@ BRB_D void blk_setup(const BrbModelConsts &c, Blk &B) {
   }
 }
 
-BRB_D unsigned blk_active_set(const BrbModelConsts &c, const Blk &B, const float (&a)[6], unsigned prev) {
+BRB_D unsigned blk_active_set(const BrbModelConsts &c, const Blk &B, const float (&a)[6], unsigned prev, float eps = 2e-4f) {
   unsigned bits = 0;
-  const float mu = c.pp[1][0], eps = 2e-4f;
+  const float mu = c.pp[1][0];
   for (int k = 0; k < B.nc; k++) {
     const float rx = B.cr[k][0], ry = B.cr[k][1], rz = B.cr[k][2];
     const float px = a[0] + a[4] * rz - a[5] * ry, py = a[1] + a[5] * rx - a[3] * rz, pz = a[2] + a[3] * ry - a[4] * rx;
@@ -526,9 +526,9 @@ BRB_D void cb_setup(const BrbModelConsts &c, const Phys &P, const Blk &B, const 
   Q.nc = n;
 }
 
-BRB_D unsigned cb_active_set(const BrbModelConsts &c, const CBSet &Q, const float (&ar)[8], const float (&ab)[6], unsigned prev) {
+BRB_D unsigned cb_active_set(const BrbModelConsts &c, const CBSet &Q, const float (&ar)[8], const float (&ab)[6], unsigned prev, float eps = 2e-4f) {
   unsigned bits = 0;
-  const float mu = c.pp[2][0], eps = 2e-4f;
+  const float mu = c.pp[2][0];
   for (int k = 0; k < Q.nc; k++) {
     const float *ra = Q.ra[k], *rb = Q.rb[k];
     const float dx = (ab[0] + ab[4] * rb[2] - ab[5] * rb[1]) - (ar[0] + ar[4] * ra[2] - ar[5] * ra[1]);
@@ -708,11 +708,14 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
     } else if (P.valid || B.nc > 0 || Q.nc > 0) {
       coupled_solve_fast(c, P, B, Q, ar, ab);
       es.csolves++;
-      const unsigned nr = P.valid ? phys_active_set<true>(c, P, ar, P.bits) : P.bits;
-      const unsigned nbl = blk_active_set(c, B, ab, B.bits), nq = cb_active_set(c, Q, ar, ab, Q.bits);
+      // rows within eps of their switching surface keep their state; when the undamped iteration starts to cycle the band
+      // is widened (x4 per extra solve from the third on), which freezes the flapping rows at a force error <= D eps
+      const float eps = it < 2 ? 2e-4f : (it == 2 ? 8e-4f : (it == 3 ? 3.2e-3f : (it == 4 ? 1.28e-2f : 5.12e-2f)));
+      const unsigned nr = P.valid ? phys_active_set<true>(c, P, ar, P.bits, eps) : P.bits;
+      const unsigned nbl = blk_active_set(c, B, ab, B.bits, eps), nq = cb_active_set(c, Q, ar, ab, Q.bits, eps);
       conv = (nr == P.bits) && (nbl == B.bits) && (nq == Q.bits);
       P.bits = nr; B.bits = nbl; Q.bits = nq;
-      if (!conv && ++it >= 5) {
+      if (!conv && ++it >= 7) {
         // the undamped active-set iteration is cycling: finish with the line-search Newton, and seed the next substep with
         // the active sets of ITS solution (otherwise the same cycle — and the same fallback — repeats substep after substep)
         float acc[14];

@@ -332,7 +332,7 @@ BRB_D void phys_setup(const BrbModelConsts &c, Phys &P) {
 // Rows within `eps` of the switching surface keep their previous state (`prev`): either choice gives the same
 // force to O(D*eps) ~ 2e-5 N, and without the hysteresis fp32 noise can flip such a row back and forth forever.
 template <int CI>
-BRB_D unsigned contact_bits(const BrbModelConsts &c, const Phys &P, const float (&a)[8], unsigned prev, float mu) {
+BRB_D unsigned contact_bits(const BrbModelConsts &c, const Phys &P, const float (&a)[8], unsigned prev, float mu, float eps) {
   if (!(P.valid & (1u << CI))) return 0u;
   const float ak = a[6 + (CI >> 1)];
   const float rx = P.cr[CI][0], ry = P.cr[CI][1], rz = P.cr[CI][2];
@@ -342,16 +342,16 @@ BRB_D unsigned contact_bits(const BrbModelConsts &c, const Phys &P, const float 
   const float z0 = pz + P.cy[CI][0];
   const float z1 = mu * (py + P.cy[CI][1]);
   const float z2 = mu * (P.cy[CI][2] - px);
-  const float eps = 2e-4f;
   const unsigned pb = prev >> (4 * CI);
   const float e0 = (pb & 1u) ? eps : -eps, e1 = (pb & 2u) ? eps : -eps, e2 = (pb & 4u) ? eps : -eps, e3 = (pb & 8u) ? eps : -eps;
   return ((unsigned)(z0 + z1 < e0) | ((unsigned)(z0 - z1 < e1) << 1) | ((unsigned)(z0 + z2 < e2) << 2) | ((unsigned)(z0 - z2 < e3) << 3)) << (4 * CI);
 }
 
 template <bool VI = false>
-BRB_D unsigned phys_active_set(const BrbModelConsts &c, const Phys &P, const float (&a)[8], unsigned prev) {
+BRB_D unsigned phys_active_set(const BrbModelConsts &c, const Phys &P, const float (&a)[8], unsigned prev, float eps = 2e-4f) {
   const float mu = VI ? c.pp[0][0] : c.mu;
-  return contact_bits<0>(c, P, a, prev, mu) | contact_bits<1>(c, P, a, prev, mu) | contact_bits<2>(c, P, a, prev, mu) | contact_bits<3>(c, P, a, prev, mu);
+  return contact_bits<0>(c, P, a, prev, mu, eps) | contact_bits<1>(c, P, a, prev, mu, eps) | contact_bits<2>(c, P, a, prev, mu, eps) |
+         contact_bits<3>(c, P, a, prev, mu, eps);
 }
 
 // ---- S_c = Pi' W_c Pi for the 16 pyramid-row patterns b of a contact: {Szz, Syz, Sxz, Syy, Sxx} (D folded in when it is a
