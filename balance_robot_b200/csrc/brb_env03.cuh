@@ -440,7 +440,7 @@ int env03_coupled_solve(const BrbModelConsts &c, const Phys &P, const GContact *
 }
 
 // ------------------------------------------------------------------------------------------------ substep driver
-struct Env03Stats { unsigned coupled, blk_contact, unsupported, fallback, csolves, coupled_last; };
+struct Env03Stats { unsigned coupled, blk_contact, unsupported, fallback, csolves, coupled_last, blk_last; };
 
 // gathers every contact of the substep into generic records and runs the coupled solve
 BRB_D int env03_coupled_substep(const BrbModelConsts &c, const Phys &P, const Blk &B, const float (*bpos)[3], const float *bdist,
@@ -685,7 +685,8 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
         if (Q.nc != qprev_nc) Q.bits = 0xFFFFFFFFu;
         if (Q.nc > 0) es.coupled++;
       }
-      es.coupled_last = Q.nc > 0 ? 1u : 0u;
+      es.coupled_last = (unsigned)Q.nc;
+      es.blk_last = B.nc > 0 ? 1u : 0u;
       qprev_nc = Q.nc;
       was = P.valid; wasn = B.nc;
       need_setup = false;
@@ -875,7 +876,7 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
   }
   KF qprev[4];
   float pstale[3];
-  Env03Stats es = {0u, 0u, 0u, 0u, 0u, 0u};
+  Env03Stats es = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
   phys03_run<BRB_MAXIT>(c, st, B, c.frame_skip, qprev, pstale, es, wmask, ctasync);
   stat[0] = c.frame_skip; stat[1] = st.n_contact; stat[2] = st.n_solve; stat[3] = st.n_nonconv; stat[7] = st.n_slots;
   stat[8] = es.coupled; stat[9] = es.blk_contact; stat[10] = es.fallback; stat[11] = es.csolves;
@@ -884,7 +885,9 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
                                : BRB_NLAND + group_rank(st.valid);
     // robots whose block was touching the chassis in the last substep (impacts last ~6 env steps) get their own bucket, so
     // the warps running the coupled assembly are not diluted by robots on the uncoupled path
-    if (es.coupled_last) stat[6] = BRB_NGROUPS - 1;
+    // (one bucket per contact count class: the coupled assembly loops over the contacts, lanes with fewer of them idle)
+    if (es.coupled_last) stat[6] = BRB_NGROUPS - 3 + (es.coupled_last <= 2u ? 0u : (es.coupled_last <= 4u ? 1u : 2u));
+    else if (es.blk_last) stat[6] = BRB_NGROUPS - 4;      // block resting / sliding on the floor: its floor contacts are a rare path
   }
 
   double qpos[16];
