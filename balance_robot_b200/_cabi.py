@@ -18,7 +18,8 @@ _EXPERIMENT_LIB = "BRB_EXPERIMENT_LIB"   # kernel-tuning experiments only (scrip
 SOURCES = ("brb_kernels.cu", "brb_cabi.cu", "brb_policy.cu")
 HEADERS = (CSRC / "brb_internal.h", CSRC / "brb_chol8.inc", CSRC / "brb_chol6.inc", CSRC / "brb_schur6.inc", CSRC / "brb_env03.cuh",
            CSRC.parent.parent / "include" / "brb.h")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+# -ftz=true: no denormal handling around MUFU.RSQ / RCP (the state is O(1); 0.895 -> 0.859 ms per step at 65,536 robots)
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-ftz=true",
               "-Xcompiler", "-fPIC", "-shared"]
 
 DONE_ROW_WORDS = 10   # include/brb.h BRB_DONE_ROW_WORDS
