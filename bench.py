@@ -35,8 +35,8 @@ ALG_FLOP_PER_ENV_STEP = FLOP_PER_SUBSTEP_CONTACT * FRAME_SKIP          # 9.25e5 
 ALG_BYTES_PER_ENV_STEP = 290.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 # dram__bytes_read.sum + dram__bytes_write.sum of brb_step_kernel<1> from the committed `ncu --set full` capture
-# (profiles/r1_step_kernel_ncu_raw.csv: 13,970,688 + 7,168 bytes for 65,536 robots) -> bytes per robot-step
-NCU_DRAM_BYTES_PER_ENV_STEP = (13970688 + 7168) / 65536
+# (profiles/r1_step_kernel_ncu_raw.csv: 13,978,112 + 12,032 bytes for 65,536 robots) -> bytes per robot-step
+NCU_DRAM_BYTES_PER_ENV_STEP = (13978112 + 12032) / 65536
 
 
 def parse_args():
