@@ -769,9 +769,7 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
 
 BRB_D double yaw_of(const double q[4]) {   // RobotBaseEnv.py:177-184
   if (q[0] == 0.0) return 0.0;
-  const double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  const double w = q[0] / n, x = q[1] / n, y = q[2] / n, z = q[3] / n;
-  return atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z));
+  return euler_xyz_of<2>(q);
 }
 
 // Env03_v2.set_block_pos_vel (env03_v2.py:25-59).  u[0..4] = target x, target z, block x/y/z_rot.

@@ -26,10 +26,12 @@
 #ifdef BRB_HOST_EMU
 #include "emu_shim.h"
 #define BRB_D static inline
+#define BRB_NOINLINE static __attribute__((noinline))
 #define __popc(x) __builtin_popcount(x)
 #else
 #include <cuda_runtime.h>
 #define BRB_D __device__ __forceinline__
+#define BRB_NOINLINE __device__ __noinline__
 #define BRB_CTA_OR(p) (__syncthreads_or(p) != 0)
 #define BRB_CTA_SYNC() __syncthreads()
 #endif
@@ -81,11 +83,30 @@ BRB_D void draw4(uint64_t seed, uint64_t env, uint32_t event, uint32_t block, do
 
 // ---------------------------------------------------------------------------------------------------
 // task-logic helpers (fp64; restate the reference Python, the oracle restates the same logic independently)
+// scipy Rotation.from_quat([x,y,z,w]).as_euler('xyz') [third party], angle `WHICH` (0 = x = pitch, 2 = z = yaw): the
+// half-angle algorithm scipy implements (Bernardes & Viollet 2022; _rotation.pyx _get_angles), operation by operation,
+// because the textbook atan2(2(wx+yz), 1-2(x^2+y^2)) equals it only to the last ulp and the 24-bit Philox uniforms put reset
+// observations on float32 rounding ties often enough for that ulp to show.  Gimbal lock (roll = +-90 deg within 1e-7) is
+// tested on the tangents instead of scipy's 2 atan2(hypot, hypot): same set up to its boundary.
+template <int WHICH>
+BRB_D double euler_xyz_of(const double q[4]) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  const double n = sqrt(x * x + y * y + z * z + w * w);
+  w /= n; x /= n; y /= n; z /= n;
+  const double a = w - y, b = x + z, c = y + w, d = z - x;
+  const double half_sum = atan2(b, a), half_diff = atan2(d, c);
+  const double sab = a * a + b * b, scd = c * c + d * d, t2 = 2.5e-15;   // tan(0.5e-7)^2
+  double r;
+  if (scd <= t2 * sab) r = WHICH == 0 ? 2 * half_sum : 0.0;
+  else if (sab <= t2 * scd) r = WHICH == 0 ? -2 * half_diff : 0.0;
+  else r = WHICH == 0 ? half_sum - half_diff : half_sum + half_diff;
+  if (r < -BRB_PI) r += 2 * BRB_PI;
+  else if (r > BRB_PI) r -= 2 * BRB_PI;
+  return r;
+}
 BRB_D double pitch_of(const double q[4]) {  // RobotBaseEnv.py:127-135
   if (q[0] == 0.0) return 0.0;
-  double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
-  double w = q[0] / n, x = q[1] / n, y = q[2] / n, z = q[3] / n;
-  return atan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y));
+  return euler_xyz_of<0>(q);
 }
 
 template <int KIND>
@@ -234,12 +255,36 @@ BRB_D float imp_of(const float *pp, float dist) {
   return pp[4] + y * (pp[5] - pp[4]);
 }
 
+// ---- the contact on/off predicate decided like fp64 (A.6: a rim point is in contact iff dist < 0 exactly).
+// A sliding contact carries O(10 N) of damping force from its first substep, so a touch-down / lift-off that fires one
+// substep early or late moves a velocity by ~1e-3.  The fp32 distances below are good to ~5e-9 m (R is built from the
+// high halves of the quaternion); whenever one of them lies within BRB_DIST_BAND of zero the four rim distances are
+// re-evaluated here in fp64 from the full compensated state and fp64 geometry constants (hi + lo floats).  Rare
+// (about one substep per touch-down), out of line, and the fp64 pipe is otherwise idle.
+#define BRB_DIST_BAND 2e-7f
+struct RimDist { float d[4]; };
+BRB_NOINLINE RimDist rim_dist_fp64(const BrbModelConsts &c, float q0s, float q0c, float q1s, float q1c, float q2s, float q2c, float q3s,
+                                   float q3c, float zs, float zc) {
+  double w = (double)q0s - (double)q0c, x = (double)q1s - (double)q1c, y = (double)q2s - (double)q2c, z = (double)q3s - (double)q3c;
+  const double inv = 1.0 / sqrt(w * w + x * x + y * y + z * z);
+  w *= inv; x *= inv; y *= inv; z *= inv;
+  const double n0 = 2 * (x * z - w * y), n1 = 2 * (y * z + w * x), n2 = 1 - 2 * (x * x + y * y);
+  const double ox = (double)c.ox + (double)c.geo_lo[0], oz = (double)c.oz + (double)c.geo_lo[1], rad = (double)c.rad + (double)c.geo_lo[2],
+               hl = (double)c.hl + (double)c.geo_lo[3];
+  const double hz = ((double)zs - (double)zc) - ((double)c.zfloor + (double)c.zfloor_lo);
+  const double common = hz + oz * n2 - rad * sqrt(n1 * n1 + n2 * n2), an = fabs(n0);
+  const double dd[4] = {common - ox * n0 - hl * an, common - ox * n0 + hl * an, common + ox * n0 - hl * an, common + ox * n0 + hl * an};
+  RimDist r;
+#pragma unroll
+  for (int k = 0; k < 4; k++) r.d[k] = dd[k] < 0.0 ? fminf((float)dd[k], -1e-30f) : fmaxf((float)dd[k], 0.f);   // the sign survives the narrowing
+  return r;
+}
+
 template <int CI, bool VI>
-BRB_D void contact_setup(const BrbModelConsts &c, Phys &P, float d0, float anx, float sa, const float (&G)[3], const float (&A)[3],
+BRB_D void contact_setup(const BrbModelConsts &c, Phys &P, float dist, float sa, const float (&G)[3], const float (&A)[3],
                          const float (&B2)[3], const float (&ww)[3]) {
   constexpr int k = CI >> 1, e = CI & 1;
   const float sg = k ? 1.f : -1.f;
-  const float dist = e ? d0 + c.hl * anx : d0 - c.hl * anx;
   if (dist < 0.f) {
     P.valid |= 1u << CI;
     const float hd = 0.5f * dist;
@@ -308,7 +353,7 @@ BRB_D void phys_setup(const BrbModelConsts &c, Phys &P) {
   const float common = hgt + (c.oz - c.rad) * n2 + c.rad * diff;
   const float anx = fabsf(n0);
   const float dmin = common - c.ox * anx - c.hl * anx;          // lowest rim point of either wheel
-  if (dmin < 0.f) {
+  if (dmin < BRB_DIST_BAND) {
     const float vy = -c.rad * n1 * irho, vz = -c.rad * n2 * irho;   // rim direction toward the floor, chassis frame: (0, vy, vz)
     const float sa = (n0 > 0.f) ? -1.f : 1.f;
     float G[3], A[3], B2[3], ww[3];
@@ -319,11 +364,15 @@ BRB_D void phys_setup(const BrbModelConsts &c, Phys &P) {
       B2[k] = P.ey[k] * n2 - P.ez[k] * n1;                       // R (0, nz, -ny)
       ww[k] = P.ex[k] * w0 + P.ey[k] * w1 + P.ez[k] * w2;        // world angular velocity
     }
-    const float dL0 = common - c.ox * n0, dR0 = common + c.ox * n0;
-    contact_setup<0, VI>(c, P, dL0, anx, sa, G, A, B2, ww);
-    contact_setup<1, VI>(c, P, dL0, anx, sa, G, A, B2, ww);
-    contact_setup<2, VI>(c, P, dR0, anx, sa, G, A, B2, ww);
-    contact_setup<3, VI>(c, P, dR0, anx, sa, G, A, B2, ww);
+    const float dL0 = common - c.ox * n0, dR0 = common + c.ox * n0, ha = c.hl * anx;
+    RimDist rd;
+    rd.d[0] = dL0 - ha; rd.d[1] = dL0 + ha; rd.d[2] = dR0 - ha; rd.d[3] = dR0 + ha;
+    if (fminf(fminf(fabsf(rd.d[0]), fabsf(rd.d[1])), fminf(fabsf(rd.d[2]), fabsf(rd.d[3]))) < BRB_DIST_BAND)
+      rd = rim_dist_fp64(c, P.q[0].s, P.q[0].c, P.q[1].s, P.q[1].c, P.q[2].s, P.q[2].c, P.q[3].s, P.q[3].c, P.p[2].s, P.p[2].c);
+    contact_setup<0, VI>(c, P, rd.d[0], sa, G, A, B2, ww);
+    contact_setup<1, VI>(c, P, rd.d[1], sa, G, A, B2, ww);
+    contact_setup<2, VI>(c, P, rd.d[2], sa, G, A, B2, ww);
+    contact_setup<3, VI>(c, P, rd.d[3], sa, G, A, B2, ww);
   }
   if (P.valid) { P.n_contact++; P.n_slots += __popc(P.valid); }
 }

@@ -54,6 +54,7 @@ class BrbModelConsts(C.Structure):
         ("pp", C.c_float * 8 * 3),
         ("blk_half", C.c_float), ("blk_mass", C.c_float), ("blk_inertia", C.c_float), ("blk_radius", C.c_float),
         ("chassis_radius", C.c_float),
+        ("geo_lo", C.c_float * 4),
         ("nq", C.c_int), ("nv", C.c_int), ("reserved", C.c_int),
     ]
 
@@ -237,6 +238,7 @@ def compile_model(spec: ModelSpec, env_kind: int, max_episode_steps: int, frame_
         raise UnsupportedModel("M_b^-1 does not have the expected block structure")
     c.ox, c.oz, c.rad, c.hl, c.zfloor = offs[1][0], offs[1][2], cyl.size[0], cyl.size[1], floor.pos[2]
     c.zfloor_lo = floor.pos[2] - float(np.float32(floor.pos[2]))
+    c.geo_lo[:] = [v - float(np.float32(v)) for v in (offs[1][0], offs[1][2], cyl.size[0], cyl.size[1])]
     c.damping, c.kv = damping, a0.kv
     c.ctrl_lo, c.ctrl_hi, c.frc_lo, c.frc_hi = a0.ctrlrange[0], a0.ctrlrange[1], a0.forcerange[0], a0.forcerange[1]
     c.mu, c.D, c.Kimp, c.Bdamp = mu, contact["D"], K * imp, Bd

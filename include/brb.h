@@ -64,6 +64,7 @@ typedef struct BrbModelConsts {
    * 2 chassis-block (impedance imp(dist) from d0, d1, width; row D = D1 * imp / (1 - imp); aref = -B vel - K imp (dist - margin)) */
   float pp[3][8];
   float blk_half, blk_mass, blk_inertia, blk_radius, chassis_radius;
+  float geo_lo[4]; /* fp64 - fp32 residuals of ox, oz, rad, hl: the contact on/off predicate is re-evaluated in fp64 near dist = 0 */
   int nq, nv, reserved;
 } BrbModelConsts;
 

@@ -49,24 +49,43 @@ void brb_ref_env_init(BrbRefEnv *e, int kind, int max_episode_steps) {
   e->attack_side_front = 1;
 }
 
+/* scipy.spatial.transform.Rotation.from_quat([x, y, z, w]).as_euler('xyz') restated (third party: scipy==1.14.1 in the
+ * reference's conda-environment.yaml:10, 1.18.1 in this image; same algorithm — Bernardes & Viollet, "Quaternion to Euler
+ * angles conversion: a direct, general and computationally efficient method", PLoS ONE 2022, as implemented in scipy's
+ * _rotation.pyx: _compute_euler_from_quat / _get_angles).  The textbook closed form atan2(2(wx+yz), 1-2(x^2+y^2)) equals
+ * it only to the last ulp; the Philox uniforms are 24-bit, which makes reset observations sit on float32 rounding ties
+ * often enough that the last ulp shows, so the algorithm is restated operation by operation (checked bit-for-bit against
+ * scipy on 4e5 quaternions, and through the reference-class fixtures in tests/test_reference_classes.py).
+ * Extrinsic 'xyz': i, j, k = 0, 1, 2, sign = +1, not symmetric.  which = 0 -> x angle (pitch), 2 -> z angle (yaw). */
+static double scipy_euler_xyz(const double *q, int which) {
+  double w = q[0], x = q[1], y = q[2], z = q[3];
+  double n = sqrt(x * x + y * y + z * z + w * w); /* from_quat normalises, summing in its own (x, y, z, w) order */
+  w /= n; x /= n; y /= n; z /= n;
+  const double pi = 3.14159265358979323846;
+  double a = w - y, b = x + z, c = y + w, d = z - x;
+  double second = 2 * atan2(hypot(c, d), hypot(a, b));
+  double half_sum = atan2(b, a), half_diff = atan2(d, c), first, third;
+  if (fabs(second) <= 1e-7) { first = 2 * half_sum; third = 0; }            /* gimbal lock: third angle set to zero */
+  else if (fabs(second - pi) <= 1e-7) { first = -2 * half_diff; third = 0; } /* (extrinsic order) */
+  else { first = half_sum - half_diff; third = half_sum + half_diff; }
+  double r = which == 0 ? first : third;                                     /* third *= sign (= +1) */
+  if (r < -pi) r += 2 * pi;
+  else if (r > pi) r -= 2 * pi;
+  return r;
+}
+
 /* RobotBaseEnv.get_pitch (RobotBaseEnv.py:127-135): x angle of scipy as_euler('xyz') of the chassis
- * xquat (closed form), 0 when w == 0 exactly; xquat is the STALE one (Q1). */
+ * xquat, 0 when w == 0 exactly; xquat is the STALE one (Q1). */
 static double true_pitch(const BrbRefEnv *e) {
   const double *q = e->d.xquat[1];
   if (q[0] == 0) return 0;
-  double w = q[0], x = q[1], y = q[2], z = q[3];
-  double n = sqrt(w * w + x * x + y * y + z * z);
-  w /= n; x /= n; y /= n; z /= n;
-  return atan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y));
+  return scipy_euler_xyz(q, 0);
 }
 
 double brb_ref_env_yaw(const BrbRefEnv *e) { /* RobotBaseEnv.py:177-184 */
   const double *q = e->d.xquat[1];
   if (q[0] == 0) return 0;
-  double w = q[0], x = q[1], y = q[2], z = q[3];
-  double n = sqrt(w * w + x * x + y * y + z * z);
-  w /= n; x /= n; y /= n; z /= n;
-  return atan2(2 * (w * z + x * y), 1 - 2 * (y * y + z * z));
+  return scipy_euler_xyz(q, 2);
 }
 
 /* get_pitch with the per-class override: v2 adds (U - 0.5) * 0.05 (env01_v2.py:16-20),

@@ -1,6 +1,8 @@
 """Env03-v2 (robot + fired block): the CUDA path's arithmetic (host emulation here, the device in test_gpu_env03.py)
 against the fp64 oracle — wheel-floor contacts with position-dependent impedance, block-floor plane-box contacts,
 chassis-block box-box impacts through the coupled 14-dof solve, and the remove / delay / re-fire state machine."""
+import ctypes as C
+
 import numpy as np
 import pytest
 
@@ -27,16 +29,34 @@ def env03_single_step(env, rv, n, seed, steps):
     assert np.array_equal(obs, o_dev)
     rng = np.random.default_rng(seed)
     er, eb, impacts = [], [], 0
+    chk = dict(steps=0, done_mismatch=0, max_rew_err=0.0, max_obs_err=0.0, refired=0, parked=0)
+    env03_single_step.last = chk
     for t in range(1, steps + 1):
         act = (helpers.pd_policy(obs) + 0.1 * rng.uniform(-1, 1, (n, 2))).astype(np.float32)
         q0, v0 = rv.get_state()
         env.set_state(q0, v0)
+        for k in range(n):      # MujocoEnv.set_state on the oracle side too (mj_forward: fresh kinematics), so the pre-step reward sees the same state
+            ref.lib().brb_ref_forward(C.byref(rv.model), C.byref(rv.env(k).d))
         us, ur = ref.env03_draws(seed, 0, n, t)
         obs, rew, done, trunc = rv.step(act, us, ur)
         o_dev, r_dev, d_dev, _ = env.step(act)
         q1, v1 = rv.get_state()
         qd, vd, _ = env.get_state()
         live = ~done.astype(bool) & ~d_dev.astype(bool)
+        # task logic on the device against the oracle: reward (pre-step state, identical by construction), termination,
+        # observation, and the remove / delay / re-fire decisions (block parked at (10, 10) or back in play)
+        chk["steps"] += n
+        chk["done_mismatch"] += int((done.astype(bool) != d_dev.astype(bool)).sum())
+        chk["max_rew_err"] = max(chk["max_rew_err"], float(np.abs(rew - r_dev).max()))
+        if live.any():
+            # obs[1] is a finite difference of the pitch over 5 ms: a 1e-6 state difference shows up as 2e-4 there
+            chk["max_obs_err"] = max(chk["max_obs_err"], float(np.abs(obs[live] - o_dev[live]).max()))
+            park_o = (np.abs(q1[live][:, 9] - 10) < 0.5) & (np.abs(q1[live][:, 10] - 10) < 0.5)
+            park_d = (np.abs(qd[live][:, 9] - 10) < 0.5) & (np.abs(qd[live][:, 10] - 10) < 0.5)
+            was_parked = (np.abs(q0[live][:, 9] - 10) < 0.5) & (np.abs(q0[live][:, 10] - 10) < 0.5)
+            chk["park_mismatch"] = chk.get("park_mismatch", 0) + int((park_o != park_d).sum())
+            chk["parked"] += int((park_o & ~was_parked).sum())
+            chk["refired"] += int((~park_o & was_parked).sum())
         impacts += sum(any(rv.env(k).d.contact[i].pair == 1 for i in range(rv.env(k).d.ncon)) for k in range(n))
         if live.any():
             eq, ev = helpers.state_errors(qd[live][:, :9], vd[live][:, :8], q1[live][:, :9], v1[live][:, :8])
@@ -71,7 +91,16 @@ def test_single_step_parity_through_impacts():
     assert np.quantile(eb, 0.95) < 1e-5 and (eb >= 3e-5).mean() <= 0.03, (np.quantile(eb, 0.95), eb.max())
     st = env.stats()
     assert st[3] == 0                                          # no active-set iteration cap hits
+    check_task_outputs(env03_single_step.last)
     env.close(); rv.close()
+
+
+def check_task_outputs(chk):
+    """reward / done / obs and the block state machine of the device path against the oracle's (same pre-step state)."""
+    assert chk["max_rew_err"] == 0.0, chk                      # f32 of the same fp64 expression on the same state: bit-equal
+    assert chk["done_mismatch"] <= 0.002 * chk["steps"], chk   # a contact-timing outlier next to the 50 degree line
+    assert chk["park_mismatch"] <= 0.01 * chk["steps"], chk    # "block slower than 0.1 m/s" is a threshold on an fp32 block state
+    assert chk["max_obs_err"] < 0.05, chk
 
 
 def test_block_cycle_remove_delay_refire():

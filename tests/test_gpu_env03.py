@@ -7,7 +7,7 @@ import torch
 import helpers
 from balance_robot_b200 import make_vec, mjcf, model
 from oracle import ref
-from test_env03_parity import env03_single_step
+from test_env03_parity import check_task_outputs, env03_single_step
 from test_gpu_parity import GpuAdapter
 
 pytestmark = pytest.mark.gpu
@@ -38,6 +38,7 @@ def test_single_step_parity_through_impacts():
     assert np.quantile(er, 0.99) < 1e-5 and (er >= 1e-5).mean() <= 0.02, (np.quantile(er, 0.99), er.max())
     assert np.quantile(eb, 0.95) < 1e-5 and (eb >= 3e-5).mean() <= 0.03, (np.quantile(eb, 0.95), eb.max())
     assert env.stats()["nonconverged"] == 0
+    check_task_outputs(env03_single_step.last)
     env.close(); rv.close()
 
 
