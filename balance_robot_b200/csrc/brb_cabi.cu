@@ -14,9 +14,10 @@
 extern "C" {
 void brb_launch_step(int kind, const BrbModelConsts *c, const BrbState *S, const BrbPerm *perm, const float *actions, float *obs, float *reward,
                      uint8_t *done, uint8_t *truncated, float *terminal_obs, float *ep_return, int32_t *ep_len,
-                     const double *replay_u, cudaStream_t stream);
+                     const double *replay_u, int max_ctas, cudaStream_t stream);
+int brb_step_resident_ctas(int kind, int device);
 void brb_launch_group(long long n, const uint8_t *key, const unsigned *hist, unsigned *cursor, int *order, unsigned *hist_zero,
-                      unsigned *cursor_zero, cudaStream_t stream);
+                      unsigned *cursor_zero, unsigned *queue_cursor, cudaStream_t stream);
 void brb_launch_reset(int kind, const BrbState *S, float *obs, const double *replay_u, cudaStream_t stream);
 void brb_launch_done_rows(long long n, const uint8_t *done, const uint8_t *truncated, const float *terminal_obs, const float *ep_return,
                           const int32_t *ep_len, unsigned *block_count, unsigned *block_base, unsigned *ticket, int *n_done,
@@ -41,8 +42,9 @@ struct BrbEnv {
   int64_t launches;
   int *order;           // [N] visit order of the next step (see BrbPerm); valid when have_order
   uint8_t *keys;        // [N] group keys published by the last step
-  unsigned *hist;       // [2][32] double-buffered histogram, [2][32] cursors behind it
+  unsigned *hist;       // [2][32] double-buffered histogram, [2][32] cursors behind it, then the step kernel's work-queue cursor
   int have_order, parity, sort_envs;
+  int max_ctas;         // resident CTAs of the step kernel on this device (0 = no work queue: one robot per thread)
   // device staging for brb_env_step_host
   float *d_actions, *d_obs, *d_reward, *d_tobs, *d_epret;
   uint8_t *d_done, *d_trunc;
@@ -105,7 +107,7 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
   const size_t NQ = (size_t)m->consts.nq, NV = (size_t)m->consts.nv;
   const size_t sz[] = {
       align_up(NQ * N * 8), align_up(NV * N * 8), align_up(4 * N * 8), align_up(8 * N * 4), align_up(N * 8), align_up(N * 8),
-      align_up(3 * N * 8), align_up(N * 4), align_up(N * 4), align_up(N * 4), align_up(BRB_NSTATS * 8), align_up(N * 4), align_up(N), align_up(4 * 32 * 4),
+      align_up(3 * N * 8), align_up(N * 4), align_up(N * 4), align_up(N * 4), align_up(BRB_NSTATS * 8), align_up(N * 4), align_up(N), align_up(4 * 32 * 4 + 64),
       // staging
       align_up(2 * N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(N), align_up(N), align_up(N * 4),
       // finished-episode compaction
@@ -153,6 +155,7 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
   e->parity = 0;
   e->have_order = 0;
   e->sort_envs = getenv("BRB_NO_SORT") ? 0 : 1;
+  e->max_ctas = getenv("BRB_NO_QUEUE") ? 0 : brb_step_resident_ctas(m->consts.env_kind, m->device);
   if (cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaFree(e->arena); free(e); return BRB_ECUDA; }
   if (cudaMallocHost(&e->h_ndone, sizeof(int32_t)) != cudaSuccess) { cudaStreamDestroy(e->host_stream); cudaFree(e->arena); free(e); return BRB_ENOMEM; }
   *out = e;
@@ -175,18 +178,22 @@ extern "C" int64_t brb_env_num_launches(const BrbEnv *e) { return e ? e->launche
 // All launches of one env object must be stream-ordered with respect to each other, as for any stateful env.
 static void launch_step(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,
                         float *terminal_obs, float *ep_return, int32_t *ep_len, const double *replay_u, cudaStream_t stream) {
-  BrbPerm perm = {nullptr, nullptr, nullptr};
-  unsigned *hist = e->hist + 32 * e->parity, *cursor = e->hist + 64 + 32 * e->parity;
+  BrbPerm perm = {nullptr, nullptr, nullptr, nullptr};
+  unsigned *hist = e->hist + 32 * e->parity, *cursor = e->hist + 64 + 32 * e->parity, *queue = e->hist + 128;
+  if (e->max_ctas > 0) {
+    perm.cursor = queue;
+    if (!e->sort_envs) cudaMemsetAsync(queue, 0, sizeof(unsigned), stream);     // otherwise the grouping kernel re-arms it
+  }
   if (e->sort_envs) {
     perm.in = e->have_order ? e->order : nullptr;
     perm.key_out = e->keys;
     perm.hist = hist;
   }
   brb_launch_step(e->model->consts.env_kind, &e->model->consts, &e->S, &perm, actions, obs, reward, done, truncated, terminal_obs,
-                  ep_return, ep_len, replay_u, stream);
+                  ep_return, ep_len, replay_u, e->max_ctas, stream);
   e->launches++;
   if (e->sort_envs) {
-    brb_launch_group(e->S.n, e->keys, hist, cursor, e->order, e->hist + 32 * (e->parity ^ 1), e->hist + 64 + 32 * (e->parity ^ 1), stream);
+    brb_launch_group(e->S.n, e->keys, hist, cursor, e->order, e->hist + 32 * (e->parity ^ 1), e->hist + 64 + 32 * (e->parity ^ 1), perm.cursor, stream);
     e->launches++;
     e->have_order = 1;
     e->parity ^= 1;

@@ -51,5 +51,6 @@ struct BrbPerm {
   const int *in;
   uint8_t *key_out;    // [N]
   unsigned *hist;      // [32] accumulated by the step kernel, zero on entry
+  unsigned *cursor;    // work-queue cursor (zero on entry; NULL = one robot per thread, fixed grid): warps pull 32 robots at a time
 };
 #endif

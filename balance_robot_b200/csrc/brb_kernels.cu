@@ -106,6 +106,10 @@ BRB_D double euler_xyz_of(const double q[4]) {
 }
 BRB_D double pitch_of(const double q[4]) {  // RobotBaseEnv.py:127-135
   if (q[0] == 0.0) return 0.0;
+#ifdef BRB_EXP_OLD_EULER
+  { double n = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]); double w = q[0] / n, x = q[1] / n, y = q[2] / n, z = q[3] / n;
+    return atan2(2 * (w * x + y * z), 1 - 2 * (x * x + y * y)); }
+#endif
   return euler_xyz_of<0>(q);
 }
 
@@ -257,22 +261,26 @@ BRB_D float imp_of(const float *pp, float dist) {
 
 // ---- the contact on/off predicate decided like fp64 (A.6: a rim point is in contact iff dist < 0 exactly).
 // A sliding contact carries O(10 N) of damping force from its first substep, so a touch-down / lift-off that fires one
-// substep early or late moves a velocity by ~1e-3.  The fp32 distances below are good to ~5e-9 m (R is built from the
-// high halves of the quaternion); whenever one of them lies within BRB_DIST_BAND of zero the four rim distances are
-// re-evaluated here in fp64 from the full compensated state and fp64 geometry constants (hi + lo floats).  Rare
-// (about one substep per touch-down), out of line, and the fp64 pipe is otherwise idle.
-#define BRB_DIST_BAND 2e-7f
+// substep early or late moves a velocity by ~1e-3.  The fp32 distances are good to ~1e-8 m at worst (R is built from the
+// high halves of the quaternion: measured rms 5e-10, max 4e-9 for the pitch term, 7e-10 / 5e-9 for the roll term);
+// whenever one of them lies within BRB_DIST_BAND of zero, the four rim distances are re-evaluated here in fp64 from the full
+// compensated state and fp64 geometry constants (hi + lo floats).  0.04 % of robot-substeps take this branch (a rim end
+// hovering near the floor does it for many substeps in a row, not only at touch-down; a warp pays for any of its 32 lanes:
+// measured +1.4 % step time at this band, +4.5 % at 2e-7), so it is kept to ~40 DFMA: no
+// fp64 sqrt or division — rho = sqrt(n1^2 + n2^2) is the fp32 value plus one Newton correction, and |q| = 1 to 1e-14
+// (normalised in fp64 at the start of the step, integrated with compensated increments).
+#ifndef BRB_DIST_BAND
+#define BRB_DIST_BAND 2e-8f
+#endif
 struct RimDist { float d[4]; };
-BRB_NOINLINE RimDist rim_dist_fp64(const BrbModelConsts &c, float q0s, float q0c, float q1s, float q1c, float q2s, float q2c, float q3s,
-                                   float q3c, float zs, float zc) {
-  double w = (double)q0s - (double)q0c, x = (double)q1s - (double)q1c, y = (double)q2s - (double)q2c, z = (double)q3s - (double)q3c;
-  const double inv = 1.0 / sqrt(w * w + x * x + y * y + z * z);
-  w *= inv; x *= inv; y *= inv; z *= inv;
+BRB_D RimDist rim_dist_fp64(const BrbModelConsts &c, const KF (&q)[4], const KF &pz, float rho32, float irho32) {
+  const double w = kjoin(q[0]), x = kjoin(q[1]), y = kjoin(q[2]), z = kjoin(q[3]);
   const double n0 = 2 * (x * z - w * y), n1 = 2 * (y * z + w * x), n2 = 1 - 2 * (x * x + y * y);
+  const double r0 = (double)rho32, rho = r0 + 0.5 * (double)irho32 * ((n1 * n1 + n2 * n2) - r0 * r0);
   const double ox = (double)c.ox + (double)c.geo_lo[0], oz = (double)c.oz + (double)c.geo_lo[1], rad = (double)c.rad + (double)c.geo_lo[2],
                hl = (double)c.hl + (double)c.geo_lo[3];
-  const double hz = ((double)zs - (double)zc) - ((double)c.zfloor + (double)c.zfloor_lo);
-  const double common = hz + oz * n2 - rad * sqrt(n1 * n1 + n2 * n2), an = fabs(n0);
+  const double hz = kjoin(pz) - ((double)c.zfloor + (double)c.zfloor_lo);
+  const double common = hz + oz * n2 - rad * rho, an = fabs(n0);
   const double dd[4] = {common - ox * n0 - hl * an, common - ox * n0 + hl * an, common + ox * n0 - hl * an, common + ox * n0 + hl * an};
   RimDist r;
 #pragma unroll
@@ -368,7 +376,7 @@ BRB_D void phys_setup(const BrbModelConsts &c, Phys &P) {
     RimDist rd;
     rd.d[0] = dL0 - ha; rd.d[1] = dL0 + ha; rd.d[2] = dR0 - ha; rd.d[3] = dR0 + ha;
     if (fminf(fminf(fabsf(rd.d[0]), fabsf(rd.d[1])), fminf(fabsf(rd.d[2]), fabsf(rd.d[3]))) < BRB_DIST_BAND)
-      rd = rim_dist_fp64(c, P.q[0].s, P.q[0].c, P.q[1].s, P.q[1].c, P.q[2].s, P.q[2].c, P.q[3].s, P.q[3].c, P.p[2].s, P.p[2].c);
+      rd = rim_dist_fp64(c, P.q, P.p[2], rho, irho);
     contact_setup<0, VI>(c, P, rd.d[0], sa, G, A, B2, ww);
     contact_setup<1, VI>(c, P, rd.d[1], sa, G, A, B2, ww);
     contact_setup<2, VI>(c, P, rd.d[2], sa, G, A, B2, ww);
@@ -856,14 +864,12 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
 #else
 #define BRB_STEP_BOUNDS(KIND) __launch_bounds__((KIND == BRB_ENV03_V2) ? BRB_BLOCK_ENV03 : BRB_BLOCK, (KIND == BRB_ENV03_V2) ? BRB_MINBLOCKS_ENV03 : BRB_MINBLOCKS)
 #endif
+// One robot of the visit order per lane: step it, publish its group key for the next step's order, add to the statistics.
 template <int KIND>
-__global__ void BRB_STEP_BOUNDS(KIND) brb_step_kernel(const __grid_constant__ BrbModelConsts c, const BrbState S, const BrbPerm perm,
-                                                const float *__restrict__ actions, float *__restrict__ obs,
-                                                float *__restrict__ reward, uint8_t *__restrict__ done,
-                                                uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs,
-                                                float *__restrict__ ep_return_out, int32_t *__restrict__ ep_len_out,
-                                                const double *__restrict__ replay_u) {
-  const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+__device__ __forceinline__ void step_batch(const BrbModelConsts &c, const BrbState &S, const BrbPerm &perm, const long long tid, const bool ctasync,
+                                           const float *__restrict__ actions, float *__restrict__ obs, float *__restrict__ reward,
+                                           uint8_t *__restrict__ done, uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs,
+                                           float *__restrict__ ep_return_out, int32_t *__restrict__ ep_len_out, const double *__restrict__ replay_u) {
   const bool live = tid < S.n;
   // envs are visited in the order of the partition built by the previous step (grounded robots by contact pattern
   // first, then the landing ones by landing time, airborne last), so a warp's lanes mostly run the same path and the
@@ -871,10 +877,6 @@ __global__ void BRB_STEP_BOUNDS(KIND) brb_step_kernel(const __grid_constant__ Br
   const long long i = live ? (perm.in ? (long long)perm.in[tid] : tid) : 0;
   unsigned stat[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const unsigned wmask = __ballot_sync(0xFFFFFFFFu, live);   // lanes of this warp that run a robot
-  for (int k = threadIdx.x; k < 16 * 5; k += blockDim.x) stab_fill(c, KIND == BRB_ENV03_V2, k);
-  // Env03-v2: when every thread of the CTA runs a robot, its warps walk the substep loop in lockstep (CTA barriers at the
-  // phase boundaries) so that they share the instruction cache: the loop body is 80 KB per trip, the L1.5 I-cache 32 KB
-  const bool ctasync = __syncthreads_and(live) != 0;
   if (live) {
     if (KIND == BRB_ENV03_V2) step_env03(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat, wmask, ctasync);
     else step_env<KIND>(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat, wmask);
@@ -915,11 +917,41 @@ __global__ void BRB_STEP_BOUNDS(KIND) brb_step_kernel(const __grid_constant__ Br
   }
 }
 
+template <int KIND>
+__global__ void BRB_STEP_BOUNDS(KIND) brb_step_kernel(const __grid_constant__ BrbModelConsts c, const BrbState S, const BrbPerm perm,
+                                                const float *__restrict__ actions, float *__restrict__ obs,
+                                                float *__restrict__ reward, uint8_t *__restrict__ done,
+                                                uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs,
+                                                float *__restrict__ ep_return_out, int32_t *__restrict__ ep_len_out,
+                                                const double *__restrict__ replay_u) {
+  for (int k = threadIdx.x; k < 16 * 5; k += blockDim.x) stab_fill(c, KIND == BRB_ENV03_V2, k);
+  // Work queue (Env01-*): the launch has at most one resident wave of CTAs and every WARP pulls the next 32 robots of the visit
+  // order from an atomic cursor until the order is exhausted.  A fixed one-robot-per-thread grid of 512 CTAs on 444 slots runs
+  // 1.15 waves: the tail wave costs a whole step-time for 13 % of the robots.
+  const bool queue = KIND != BRB_ENV03_V2 && perm.cursor != nullptr;
+  long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  // Env03-v2: when every thread of the CTA runs a robot, its warps walk the substep loop in lockstep (CTA barriers at the
+  // phase boundaries) so that they share the instruction cache: the loop body is 80 KB per trip, the L1.5 I-cache 32 KB
+  const bool ctasync = __syncthreads_and(tid < S.n) != 0;
+  for (;;) {
+    if (queue) {
+      unsigned base = 0;
+      if ((threadIdx.x & 31u) == 0u) base = atomicAdd(perm.cursor, 32u);
+      base = __shfl_sync(0xFFFFFFFFu, base, 0);
+      if ((long long)base >= S.n) break;
+      tid = (long long)base + (threadIdx.x & 31u);
+    }
+    step_batch<KIND>(c, S, perm, tid, ctasync && !queue, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u);
+    if (!queue) break;
+  }
+}
+
 // Counting sort of the envs by group key -> visit order of the next step (descending key).  hist[] was accumulated by the step kernel;
 // order inside a bucket is arbitrary (atomic cursor) and irrelevant to the results, which are per-env deterministic.
 __global__ void brb_group_kernel(long long n, const uint8_t *__restrict__ key, const unsigned *__restrict__ hist, unsigned *cursor,
-                                 int *__restrict__ order, unsigned *hist_zero, unsigned *cursor_zero) {
+                                 int *__restrict__ order, unsigned *hist_zero, unsigned *cursor_zero, unsigned *queue_cursor) {
   const long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (tid == 0 && queue_cursor) *queue_cursor = 0u;     // the step kernel's work-queue cursor, for the next launch
   const bool live = tid < n;
   const unsigned k = live ? key[tid] : 31u;
   // most expensive groups first (grounded robots, then the landing ones, airborne last): the cheap CTAs fill the tail of
@@ -1063,10 +1095,25 @@ __global__ void brb_ffma_probe_kernel(float *out, int iters, float a, float b) {
 
 // ---------------------------------------------------------------------------------------------------
 // launch wrappers used by the C-ABI translation unit (brb_cabi.cu)
+extern "C" int brb_step_resident_ctas(int kind, int device) {
+  int per_sm = 0, sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  cudaError_t e = cudaSuccess;
+  switch (kind) {
+    case BRB_ENV01_V1: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, brb_step_kernel<BRB_ENV01_V1>, BRB_BLOCK, 0); break;
+    case BRB_ENV01_V2: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, brb_step_kernel<BRB_ENV01_V2>, BRB_BLOCK, 0); break;
+    case BRB_ENV01_V3: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, brb_step_kernel<BRB_ENV01_V3>, BRB_BLOCK, 0); break;
+    default: e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, brb_step_kernel<BRB_ENV03_V2>, BRB_BLOCK_ENV03, 0); break;
+  }
+  if (e != cudaSuccess || per_sm < 1 || sms < 1) { cudaGetLastError(); return 0; }
+  return per_sm * sms;
+}
+
 extern "C" void brb_launch_step(int kind, const BrbModelConsts *c, const BrbState *S, const BrbPerm *perm, const float *actions, float *obs, float *reward,
                                 uint8_t *done, uint8_t *truncated, float *terminal_obs, float *ep_return, int32_t *ep_len,
-                                const double *replay_u, cudaStream_t stream) {
-  const unsigned grid = (unsigned)((S->n + BRB_BLOCK - 1) / BRB_BLOCK);
+                                const double *replay_u, int max_ctas, cudaStream_t stream) {
+  unsigned grid = (unsigned)((S->n + BRB_BLOCK - 1) / BRB_BLOCK);
+  if (perm->cursor != nullptr && kind != BRB_ENV03_V2 && grid > (unsigned)max_ctas) grid = (unsigned)max_ctas;   // one resident wave, warps pull work
   switch (kind) {
     case BRB_ENV01_V1:
       brb_step_kernel<BRB_ENV01_V1><<<grid, BRB_BLOCK, 0, stream>>>(*c, *S, *perm, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
@@ -1088,8 +1135,8 @@ extern "C" void brb_tripstats(unsigned long long *out) { cudaMemcpyFromSymbol(ou
 #endif
 
 extern "C" void brb_launch_group(long long n, const uint8_t *key, const unsigned *hist, unsigned *cursor, int *order, unsigned *hist_zero,
-                                 unsigned *cursor_zero, cudaStream_t stream) {
-  brb_group_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, key, hist, cursor, order, hist_zero, cursor_zero);
+                                 unsigned *cursor_zero, unsigned *queue_cursor, cudaStream_t stream) {
+  brb_group_kernel<<<(unsigned)((n + 255) / 256), 256, 0, stream>>>(n, key, hist, cursor, order, hist_zero, cursor_zero, queue_cursor);
 }
 
 extern "C" void brb_launch_done_rows(long long n, const uint8_t *done, const uint8_t *truncated, const float *terminal_obs, const float *ep_return,

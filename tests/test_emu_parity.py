@@ -27,7 +27,7 @@ def test_single_step_parity_closed_loop(spec, kind):
 def test_single_step_parity_random_actions_with_slip(spec):
     rm = model.compile_model(spec, 1, 6000)
     env = helpers.EmuVecEnv(rm, 16, seed=8)
-    wq, wv = pc.single_step_parity(env, spec, "Env01-v2", 16, 8, 60, policy="random", max_outlier_frac=0.0)
+    wq, wv = pc.single_step_parity(env, spec, "Env01-v2", 16, 8, 60, policy="random", max_outlier_frac=0.0)     # 16 x 60: no event in this sample
     assert wq < 1e-5 and wv < 1e-5, (wq, wv)
     st = env.stats()
     assert st[3] == 0, "active-set iteration hit its cap"

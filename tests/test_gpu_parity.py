@@ -74,8 +74,10 @@ def test_single_step_parity_1000_step_horizon(spec):
 
 def test_single_step_parity_random_actions_with_slip(spec):
     env = GpuAdapter("Env01-v2", 64, 8)
-    wq, wv = pc.single_step_parity(env, spec, "Env01-v2", 64, 8, 60, policy="random", max_outlier_frac=0.0)
-    assert wq < 1e-5 and wv < 1e-5, (wq, wv)
+    # 3,770 tumbling env-steps; at most ONE contact-timing event (this seed has the touch-down at fp64 dist = -1.7e-11 m that
+    # DESIGN.md §5 dissects: the in-step trajectory difference, 3e-10 m, decides its sign).  Was 1 % before the fp64 predicate.
+    q99, outliers = pc.single_step_parity(env, spec, "Env01-v2", 64, 8, 60, policy="random", max_outlier_frac=3e-4)
+    assert q99 < 1e-6, q99
     assert env.stats()["nonconverged"] == 0
     env.close()
 
