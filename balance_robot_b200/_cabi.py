@@ -15,8 +15,8 @@ from .model import BrbModelConsts
 CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "libbrb_cuda.so"
 _EXPERIMENT_LIB = "BRB_EXPERIMENT_LIB"   # kernel-tuning experiments only (scripts/): alternative build of the SAME sources
-SOURCES = ("brb_kernels.cu", "brb_cabi.cu", "brb_policy.cu")
-HEADERS = (CSRC / "brb_internal.h", CSRC / "brb_chol8.inc", CSRC / "brb_chol6.inc", CSRC / "brb_schur6.inc", CSRC / "brb_env03.cuh",
+SOURCES = ("brb_kernels.cu", "brb_cabi.cu", "brb_policy.cu", "brb_policy_tc.cu")
+HEADERS = (CSRC / "brb_internal.h", CSRC / "brb_policy_layout.h", CSRC / "brb_chol8.inc", CSRC / "brb_chol6.inc", CSRC / "brb_schur6.inc", CSRC / "brb_env03.cuh",
            CSRC.parent.parent / "include" / "brb.h")
 # -ftz=true: no denormal handling around MUFU.RSQ / RCP (the state is O(1); 0.895 -> 0.859 ms per step at 65,536 robots)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-ftz=true",
@@ -30,7 +30,7 @@ STAT_NAMES = ("substeps", "contact_substeps", "solves", "nonconverged", "unsuppo
 EXPORTS = (
     "brb_version", "brb_strerror", "brb_model_create", "brb_model_destroy", "brb_env_create", "brb_env_destroy",
     "brb_env_reset_all", "brb_env_step", "brb_env_step_host", "brb_env_step_host_compact", "brb_env_get_state", "brb_env_set_state",
-    "brb_env_get_elapsed", "brb_env_get_stats", "brb_env_num_envs", "brb_env_num_launches", "brb_fp32_peak_flops", "brb_policy_act", "brb_ppo_grad",
+    "brb_env_get_elapsed", "brb_env_get_stats", "brb_env_num_envs", "brb_env_num_launches", "brb_fp32_peak_flops", "brb_policy_act", "brb_ppo_grad", "brb_adam_clip_step", "brb_policy_value_masked", "brb_ppo_tc_fault",
 )
 
 
@@ -93,6 +93,9 @@ def lib() -> C.CDLL:
     L.brb_fp32_peak_flops.argtypes = [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]
     L.brb_policy_act.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, vp]
     L.brb_ppo_grad.argtypes = [vp] * 7 + [i64, vp, C.c_float, C.c_float, C.c_float, vp, vp, vp]
+    L.brb_ppo_tc_fault.argtypes = [C.c_int]
+    L.brb_policy_value_masked.argtypes = [vp, vp, vp, i64, vp, vp]
+    L.brb_adam_clip_step.argtypes = [vp] * 4 + [i64] + [C.c_float] * 4 + [i64, C.c_float, C.c_float, vp, vp]
     _lib = L
     return L
 

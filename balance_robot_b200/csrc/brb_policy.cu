@@ -14,21 +14,13 @@
 //   pi.W1[64][6] pi.b1[64] pi.W2[64][64] pi.b2[64] | vf.W1[64][6] vf.b1[64] vf.W2[64][64] vf.b2[64] |
 //   action_net.W[2][64] action_net.b[2] | value_net.W[1][64] value_net.b[1] | log_std[2]
 #include <cuda_runtime.h>
+#include <math.h>
 #include <stdint.h>
+#include <stdlib.h>
 
 #include "../../include/brb.h"
 
-#define PH 64                       // hidden width
-#define PIN 6                       // observation size
-#define TOWER (PH * PIN + PH + PH * PH + PH)
-#define OFF_PI 0
-#define OFF_VF TOWER
-#define OFF_AW (2 * TOWER)
-#define OFF_AB (OFF_AW + 2 * PH)
-#define OFF_VW (OFF_AB + 2)
-#define OFF_VB (OFF_VW + PH)
-#define OFF_LS (OFF_VB + 1)
-#define NPARAM (OFF_LS + 2)         // 9,413 = BRB_POLICY_NPARAM
+#include "brb_policy_layout.h"
 
 static_assert(NPARAM == BRB_POLICY_NPARAM, "parameter block layout");
 
@@ -82,11 +74,12 @@ __device__ __forceinline__ void tower(const float *__restrict__ sp, int off, int
 __global__ void __launch_bounds__(128) brb_policy_act_kernel(const float *__restrict__ params, const float *__restrict__ obs,
                                                              const float *__restrict__ noise, long long n, float *__restrict__ actions,
                                                              float *__restrict__ actions_clipped, float *__restrict__ values,
-                                                             float *__restrict__ logp) {
+                                                             float *__restrict__ logp, const uint8_t *__restrict__ mask) {
   __shared__ __align__(16) float sp[(NPARAM + 3) & ~3];
   for (int k = threadIdx.x; k < NPARAM; k += blockDim.x) sp[k] = params[k];
   __syncthreads();
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    if (mask && !mask[i]) { values[i] = 0.f; continue; }      // masked critic call: only the flagged rows are evaluated
     float x[PIN];
 #pragma unroll
     for (int k = 0; k < PIN; k++) x[k] = obs[i * PIN + k];
@@ -123,7 +116,25 @@ extern "C" int brb_policy_act(const float *params, const float *obs, const float
   }
   const long long tiles = (n + 127) / 128, cap = (long long)sms * 8;      // grid-stride: a few CTAs per SM re-use their weight copy
   brb_policy_act_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 128, 0, (cudaStream_t)stream>>>(params, obs, noise, n, actions, actions_clipped,
-                                                                                               values, logp);
+                                                                                               values, logp, nullptr);
+  if (cudaGetLastError() != cudaSuccess) return BRB_ECUDA;
+  return BRB_OK;
+}
+
+// Critic only, and only for the rows whose mask byte is non-zero (values of the others = 0): V(terminal_observation) for the
+// TimeLimit bootstrap, where at most N / max_episode_steps rows per step are truncated.  No host-side test of "any truncated?"
+// (that would put a sync into every step of the rollout): unflagged warps leave after one byte load per lane.
+extern "C" int brb_policy_value_masked(const float *params, const float *obs, const uint8_t *mask, int64_t n, float *values, void *stream) {
+  if (!params || !obs || !mask || !values || n < 0) return BRB_EINVAL;
+  if (n == 0) return BRB_OK;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
+    cudaGetLastError();
+    return BRB_ECUDA;
+  }
+  const long long tiles = (n + 127) / 128, cap = (long long)sms * 8;
+  brb_policy_act_kernel<<<(unsigned)(tiles < cap ? tiles : cap), 128, 0, (cudaStream_t)stream>>>(params, obs, nullptr, n, nullptr, nullptr, values,
+                                                                                               nullptr, mask);
   if (cudaGetLastError() != cudaSuccess) return BRB_ECUDA;
   return BRB_OK;
 }
@@ -400,6 +411,19 @@ __global__ void __launch_bounds__(128, 2) brb_ppo_grad_kernel(const float *__res
   if (ACTOR && blockIdx.x == 0 && tid < 2 && ent_coef != 0.f) atomicAdd(grad + OFF_LS + tid, -ent_coef);
 }
 
+// tensor-core version (brb_policy_tc.cu)
+extern "C" int brb_ppo_grad_tc_launch(const float *params, const float *obs, const float *actions, const float *old_logp, const float *adv,
+                                      const float *returns, const int64_t *idx, int64_t mb, const float *adv_stats, float clip_range, float vf_coef,
+                                      float ent_coef, float *grad, float *stats, int *fault, int sms, cudaStream_t s);
+static int *g_tc_fault[16];      // per device: set to 1 by the tcgen05 kernel if a (bounded) pipeline wait timed out
+
+extern "C" int brb_ppo_tc_fault(int device) {
+  if (device < 0 || device >= 16 || !g_tc_fault[device]) return 0;
+  int v = 0;
+  if (cudaMemcpy(&v, g_tc_fault[device], sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return v;
+}
+
 extern "C" int brb_ppo_grad(const float *params, const float *obs, const float *actions, const float *old_logp, const float *adv,
                             const float *returns, const int64_t *idx, int64_t mb, const float *adv_stats, float clip_range, float vf_coef,
                             float ent_coef, float *grad, float *stats, void *stream) {
@@ -408,6 +432,14 @@ extern "C" int brb_ppo_grad(const float *params, const float *obs, const float *
   if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) {
     cudaGetLastError();
     return BRB_ECUDA;
+  }
+  const bool no_tc = getenv("BRB_PPO_NO_TC") != nullptr;            // A/B measurements only: the FFMA version of the same gradient
+  if (!no_tc && dev < 16) {
+    if (!g_tc_fault[dev]) {
+      if (cudaMalloc(&g_tc_fault[dev], sizeof(int)) != cudaSuccess || cudaMemset(g_tc_fault[dev], 0, sizeof(int)) != cudaSuccess) { cudaGetLastError(); return BRB_ENOMEM; }
+    }
+    return brb_ppo_grad_tc_launch(params, obs, actions, old_logp, adv, returns, idx, mb, adv_stats, clip_range, vf_coef, ent_coef, grad, stats,
+                                  g_tc_fault[dev], sms, (cudaStream_t)stream);
   }
   const long long tiles = (mb + 127) / 128, cap = 2LL * sms;
   const unsigned grid = (unsigned)(tiles < cap ? tiles : cap);
@@ -422,6 +454,59 @@ extern "C" int brb_ppo_grad(const float *params, const float *obs, const float *
                                                      clip_range, vf_coef, ent_coef, grad, stats);
   brb_ppo_grad_kernel<0><<<grid, 128, smem, s>>>(params, obs, actions, old_logp, adv, returns, (const long long *)idx, mb, adv_stats,
                                                      clip_range, vf_coef, ent_coef, grad, stats);
+  if (cudaGetLastError() != cudaSuccess) return BRB_ECUDA;
+  return BRB_OK;
+}
+
+// ================================================================================================================
+// One optimiser step on the flat parameter block, fused: gradient averaging over the ranks, global-norm clipping and Adam.
+//
+// Replaces, for one minibatch of SB3's PPO.train() (third party; reference src/sb_rl.py:63-71 runs it with SB3's defaults):
+//   th.nn.utils.clip_grad_norm_(policy.parameters(), max_grad_norm)      total = ||g||_2 ; g *= min(1, max_norm / (total + 1e-6))
+//   policy.optimizer.step()                                              torch.optim.Adam (no weight decay, no amsgrad)
+// which in PyTorch is ~25 small launches (per-parameter norms, stack, norm, clamp, foreach mul, foreach Adam pieces) and
+// a host round trip per tensor list.  The parameter block is 9,413 floats, so one CTA does it in one launch:
+//   g = grad * grad_scale (1 / world after the all-reduce sum); block-reduce sum g^2; clip; m, v, p updated in place;
+//   grad is zeroed for the next minibatch's accumulation (saves the memset launch).
+// `step` is the 1-based Adam step count.  All pointers are device pointers.
+__global__ void __launch_bounds__(1024) brb_adam_clip_kernel(float *__restrict__ params, float *__restrict__ grad, float *__restrict__ m,
+                                                             float *__restrict__ v, int n, float lr, float beta1, float beta2, float eps,
+                                                             float bias1, float bias2_sqrt, float max_norm, float grad_scale,
+                                                             float *__restrict__ norm_out) {
+  __shared__ float red[32];
+  __shared__ float coef_s;
+  float ss = 0.f;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) { const float g = grad[k] * grad_scale; ss = fmaf(g, g, ss); }
+  ss = warp_sum_f(ss);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float t = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.f;
+    t = warp_sum_f(t);
+    if (threadIdx.x == 0) {
+      const float total = sqrtf(t);
+      coef_s = max_norm > 0.f ? fminf(1.f, max_norm / (total + 1e-6f)) : 1.f;
+      if (norm_out) *norm_out = total;
+    }
+  }
+  __syncthreads();
+  const float coef = coef_s * grad_scale, step_size = lr / bias1;
+  for (int k = threadIdx.x; k < n; k += blockDim.x) {
+    const float g = grad[k] * coef;
+    const float mk = beta1 * m[k] + (1.f - beta1) * g;
+    const float vk = beta2 * v[k] + (1.f - beta2) * g * g;
+    m[k] = mk; v[k] = vk;
+    params[k] -= step_size * mk / (sqrtf(vk) / bias2_sqrt + eps);
+    grad[k] = 0.f;
+  }
+}
+
+extern "C" int brb_adam_clip_step(float *params, float *grad, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
+                                  int64_t step, float max_grad_norm, float grad_scale, float *norm_out, void *stream) {
+  if (!params || !grad || !m || !v || n <= 0 || n > (1 << 24) || step < 1) return BRB_EINVAL;
+  const double b1 = 1.0 - pow((double)beta1, (double)step), b2 = 1.0 - pow((double)beta2, (double)step);
+  brb_adam_clip_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(params, grad, m, v, (int)n, lr, beta1, beta2, eps, (float)b1, (float)sqrt(b2),
+                                                             max_grad_norm, grad_scale, norm_out);
   if (cudaGetLastError() != cudaSuccess) return BRB_ECUDA;
   return BRB_OK;
 }

@@ -113,6 +113,19 @@ class MlpPolicy(nn.Module):
         return values
 
     @torch.no_grad()
+    def value_masked_fused(self, obs, mask, params: torch.Tensor):
+        """critic values of the rows where mask (uint8) != 0, zero elsewhere (csrc/brb_policy.cu: brb_policy_value_masked)."""
+        import ctypes as C
+        from . import _cabi
+        obs = obs.to(torch.float32).contiguous()
+        mask = mask.to(torch.uint8).contiguous()
+        values = torch.empty(obs.shape[0], device=obs.device)
+        with torch.cuda.device(obs.device):
+            _cabi.check(_cabi.lib().brb_policy_value_masked(params.data_ptr(), obs.data_ptr(), mask.data_ptr(), obs.shape[0], values.data_ptr(),
+                                                            C.c_void_p(torch.cuda.current_stream(obs.device).cuda_stream)), "brb_policy_value_masked")
+        return values
+
+    @torch.no_grad()
     def act(self, obs, deterministic: bool = False, generator: Optional[torch.Generator] = None):
         mean, log_std = self._dist(obs)
         if deterministic:
@@ -178,7 +191,10 @@ class PPO:
         self.gen = torch.Generator(device=self.device).manual_seed(config.seed * 1000003 + rank)
         self.num_timesteps = 0
         self.fused_update = True      # CUDA: minibatch forward + loss + backward through brb_ppo_grad (False: autograd)
-        self._gflat = None
+        self._gflat = self._pflat = None
+        self._adam_t = 0
+        if self.device.type == "cuda" and self.policy.action_net.in_features == 64:
+            self._flatten_parameters()
         self._obs = None
         self.ep_stats = {"return_sum": 0.0, "len_sum": 0.0, "count": 0.0}
         n, T = env.num_envs, config.n_steps
@@ -186,6 +202,49 @@ class PPO:
         self.buf = {"obs": torch.zeros((T, n, 6), device=dv), "actions": torch.zeros((T, n, 2), device=dv),
                     "logp": torch.zeros((T, n), device=dv), "values": torch.zeros((T, n), device=dv),
                     "rewards": torch.zeros((T, n), device=dv), "dones": torch.zeros((T, n), device=dv)}
+
+    # ---- flat parameter / gradient / Adam-moment blocks for the fused CUDA update (csrc/brb_policy.cu)
+    def _flatten_parameters(self) -> None:
+        """Re-homes every parameter (and its .grad) as a view of ONE flat fp32 block in the layout brb_policy_act /
+        brb_ppo_grad / brb_adam_clip_step read, so no packing, no per-parameter launches and no copies are needed."""
+        from . import _cabi
+        ps = self.policy.packed_parameters()
+        flat = torch.cat([p.detach().reshape(-1) for p in ps]).float().contiguous()
+        assert flat.numel() == _cabi.POLICY_NPARAM
+        self._pflat, self._gflat = flat, torch.zeros_like(flat)
+        self._m, self._v = torch.zeros_like(flat), torch.zeros_like(flat)
+        self._gstats = torch.zeros(4, device=self.device)
+        self._gnorm = torch.zeros(1, device=self.device)
+        off = 0
+        for p in ps:
+            k = p.numel()
+            p.data = flat[off:off + k].view_as(p)
+            p.grad = self._gflat[off:off + k].view_as(p)
+            off += k
+
+    def _export_adam_state(self) -> None:
+        """flat Adam moments -> the torch optimizer's per-parameter state (for checkpoints in SB3's layout)."""
+        if self._pflat is None or self._adam_t == 0:
+            return
+        off = 0
+        for p in self.policy.packed_parameters():
+            k = p.numel()
+            self.optimizer.state[p] = {"step": torch.tensor(float(self._adam_t)), "exp_avg": self._m[off:off + k].view_as(p).clone(),
+                                       "exp_avg_sq": self._v[off:off + k].view_as(p).clone()}
+            off += k
+
+    def _import_adam_state(self) -> None:
+        if self._pflat is None:
+            return
+        off = 0
+        for p in self.policy.packed_parameters():
+            k = p.numel()
+            st = self.optimizer.state.get(p)
+            if st and "exp_avg" in st:
+                self._m[off:off + k].copy_(st["exp_avg"].reshape(-1))
+                self._v[off:off + k].copy_(st["exp_avg_sq"].reshape(-1))
+                self._adam_t = int(float(st["step"]))
+            off += k
 
     # ---- distributed helpers (no-ops for world_size 1)
     def _all_reduce_(self, t: torch.Tensor) -> torch.Tensor:
@@ -215,7 +274,7 @@ class PPO:
         ep_len = torch.zeros((), device=self.device, dtype=torch.float64)
         ep_cnt = torch.zeros((), device=self.device, dtype=torch.float64)
         fused = self.device.type == "cuda" and self.policy.action_net.in_features == 64
-        params = self.policy.pack_params() if fused else None      # the weights do not change during a rollout
+        params = (self._pflat if self._pflat is not None else self.policy.pack_params()) if fused else None   # the weights do not change during a rollout
         for t in range(cfg.n_steps):
             if fused:       # one launch: towers + sample + log-prob + value + clipped copy (csrc/brb_policy.cu)
                 actions, values, logp, clipped = self.policy.act_fused(self._obs, generator=self.gen, params=params)
@@ -230,12 +289,15 @@ class PPO:
             done_f = done.to(torch.float32)
             rew = rew.clone()
             # TimeLimit bootstrap: reward += gamma * V(terminal_observation) where the episode was truncated
-            # (evaluated for every env and masked: a `trunc.any()` test would put a host sync into every step of the rollout;
-            # terminal_observation rows of envs that never finished are zeros, so the masked product is finite)
+            # (a `trunc.any()` test would put a host sync into every step of the rollout; the CUDA path evaluates the critic only for the
+            # flagged rows on the device, <= N / max_episode_steps of them per step; the CPU path evaluates every row and masks)
             if hasattr(infos, "truncated"):
                 with torch.no_grad():
-                    tv = self.policy.value_fused(infos.terminal_observation, params) if fused else self.policy.value(infos.terminal_observation)
-                rew = rew + cfg.gamma * tv * infos.truncated.to(rew.dtype)
+                    if fused:
+                        tv = self.policy.value_masked_fused(infos.terminal_observation, infos.truncated, params)
+                    else:
+                        tv = self.policy.value(infos.terminal_observation) * infos.truncated.to(rew.dtype)
+                rew = rew + cfg.gamma * tv
             b["rewards"][t].copy_(rew)
             b["dones"][t].copy_(done_f)
             if hasattr(infos, "episode_return"):
@@ -256,26 +318,22 @@ class PPO:
 
     # ---- update
     def _train_fused(self) -> Dict[str, float]:
-        """train() with forward + loss + backward of a minibatch as two CUDA launches (csrc/brb_policy.cu: brb_ppo_grad, one
-        per tower) instead of the autograd graph; Adam, gradient clipping and the all-reduce stay in PyTorch."""
+        """train() as three CUDA launches per minibatch (csrc/brb_policy.cu): brb_ppo_grad (forward + loss + backward, one launch per
+        tower) and brb_adam_clip_step (gradient averaging, global-norm clipping and Adam on the flat parameter block); across
+        ranks one all-reduce of the flat gradient in between."""
         import ctypes as C
         from . import _cabi
-        cfg, b, pol = self.cfg, self.buf, self.policy
+        cfg, b = self.cfg, self.buf
         T, n = b["rewards"].shape
         total = T * n
         mb = total // cfg.n_minibatches
         obs, act = b["obs"].reshape(total, 6), b["actions"].reshape(total, 2)
         oldlp, adv, ret = b["logp"].reshape(total), b["adv"].reshape(total).contiguous(), b["ret"].reshape(total).contiguous()
-        if getattr(self, "_gflat", None) is None:
-            self._gflat = torch.zeros(_cabi.POLICY_NPARAM, device=self.device)
-            self._gstats = torch.zeros(4, device=self.device)
-            off = 0
-            for p in pol.packed_parameters():            # every .grad is a view of the flat gradient the kernel fills
-                p.grad = self._gflat[off:off + p.numel()].view_as(p)
-                off += p.numel()
         L, stream = _cabi.lib(), C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
-        logs = torch.zeros(4, device=self.device)
         unit = torch.tensor([0.0, 1.0], device=self.device)
+        lr, eps = self.optimizer.param_groups[0]["lr"], self.optimizer.param_groups[0]["eps"]
+        b1, b2 = self.optimizer.param_groups[0]["betas"]
+        self._gflat.zero_(); self._gstats.zero_()
         updates = 0
         for _ in range(cfg.n_epochs):
             perm = torch.randperm(total, device=self.device, generator=self.gen)
@@ -283,22 +341,22 @@ class PPO:
                 idx = perm[k * mb:(k + 1) * mb]
                 if cfg.normalize_advantage and mb > 1:
                     a = adv[idx]
-                    astats = torch.stack([a.mean(), 1.0 / (a.std() + 1e-8)])
+                    sd, mu = torch.std_mean(a)
+                    astats = torch.stack([mu, 1.0 / (sd + 1e-8)])
                 else:
                     astats = unit
-                params = pol.pack_params()
-                self._gflat.zero_(); self._gstats.zero_()
                 with torch.cuda.device(self.device):
-                    _cabi.check(L.brb_ppo_grad(params.data_ptr(), obs.data_ptr(), act.data_ptr(), oldlp.data_ptr(), adv.data_ptr(),
+                    _cabi.check(L.brb_ppo_grad(self._pflat.data_ptr(), obs.data_ptr(), act.data_ptr(), oldlp.data_ptr(), adv.data_ptr(),
                                                ret.data_ptr(), idx.data_ptr(), mb, astats.data_ptr(), cfg.clip_range, cfg.vf_coef,
                                                cfg.ent_coef, self._gflat.data_ptr(), self._gstats.data_ptr(), stream), "brb_ppo_grad")
-                if self.world > 1:
-                    self._all_reduce_(self._gflat).div_(self.world)
-                torch.nn.utils.clip_grad_norm_(pol.parameters(), cfg.max_grad_norm)
-                self.optimizer.step()
-                logs += self._gstats
+                    if self.world > 1:
+                        self._all_reduce_(self._gflat)
+                    self._adam_t += 1
+                    _cabi.check(L.brb_adam_clip_step(self._pflat.data_ptr(), self._gflat.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
+                                                     self._pflat.numel(), lr, b1, b2, eps, self._adam_t, cfg.max_grad_norm or 0.0,
+                                                     1.0 / self.world, self._gnorm.data_ptr(), stream), "brb_adam_clip_step")
                 updates += 1
-        vals = (logs / max(1, updates)).tolist()
+        vals = (self._gstats / max(1, updates)).tolist()
         return dict(zip(("policy_loss", "value_loss", "approx_kl", "clip_fraction"), vals))
 
     def train(self) -> Dict[str, float]:
@@ -373,6 +431,7 @@ class PPO:
             bio = io.BytesIO()
             torch.save(obj, bio)
             return bio.getvalue()
+        self._export_adam_state()
         with zipfile.ZipFile(path, "w") as z:
             z.writestr("data", json.dumps(data, indent=1))
             z.writestr("policy.pth", blob({k: v.detach().cpu() for k, v in self.policy.state_dict().items()}))
@@ -396,6 +455,7 @@ class PPO:
         if opt:
             try:
                 self.optimizer.load_state_dict(opt)
+                self._import_adam_state()
             except Exception:
                 pass
         self.num_timesteps = int(data.get("num_timesteps", 0))

@@ -34,9 +34,16 @@ FRAME_SKIP = 250
 ALG_FLOP_PER_ENV_STEP = FLOP_PER_SUBSTEP_CONTACT * FRAME_SKIP          # 9.25e5 ("9.3e5" in SURVEY.md)
 ALG_BYTES_PER_ENV_STEP = 290.0
 NOMINAL_FP32_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
-# dram__bytes_read.sum + dram__bytes_write.sum of brb_step_kernel<1> from the committed `ncu --set full` capture
-# (profiles/r1_step_kernel_ncu_raw.csv: 13,978,112 + 12,032 bytes for 65,536 robots) -> bytes per robot-step
-NCU_DRAM_BYTES_PER_ENV_STEP = (13978112 + 12032) / 65536
+# Counters of brb_step_kernel<Env01_v2> from the committed `ncu --set full` capture of this command (one launch, 65,536 robots):
+# profiles/<round>_step_kernel_ncu_summary.json is written by scripts/make_profile_summaries.py from the raw page next to it.
+def load_ncu_summary():
+    for name in ("r2_step_kernel_ncu_summary.json", "r1_step_kernel_ncu_summary.json"):
+        f = ROOT / "profiles" / name
+        if f.exists():
+            d = json.load(open(f))
+            d["source"] = f"profiles/{name}"
+            return d
+    return None
 
 
 def parse_args():
@@ -56,6 +63,9 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--actions", default="random", choices=["random", "policy"],
                     help="random: U(-1,1)^2 resident in HBM (BASELINE configs[1]); policy: on-device MlpPolicy inference every step")
+    ap.add_argument("--sustained-s", type=float, default=1.2, help="length of the back-to-back `sustained` sub-run (0 = skip)")
+    ap.add_argument("--ppo-envs-per-gpu", type=int, default=1048576, help="envs per GPU of the `ppo` sub-record (BASELINE configs[4]; 0 = skip)")
+    ap.add_argument("--ppo-iters", type=int, default=2)
     return ap.parse_args()
 
 
@@ -261,8 +271,66 @@ def run_b200(args, rank, world, local_rank):
                        "device, 40 B per finished env; SB3 infos list built lazily)"}
         env_h.close()
 
+    # ---- sustained: >= --sustained-s seconds of back-to-back steps in the same run (same per-step events, L2 flushed between)
+    sustained = None
+    if args.sustained_s > 0:
+        ksus = max(args.steps, int(args.sustained_s / (total_ms / args.steps * 1e-3)) + 1)
+        ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ksus)]
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        sampler2 = ClockSampler(local_rank) if rank == 0 else None
+        w0 = time.perf_counter()
+        for k in range(ksus):
+            flush.fill_(k & 0xFF)
+            ev2[k][0].record()
+            one_step(k)
+            ev2[k][1].record()
+        torch.cuda.synchronize(dev)
+        w1 = time.perf_counter() - w0
+        clocks2 = sampler2.stop() if sampler2 else None
+        sus_ms = sum(a.elapsed_time(b) for a, b in ev2)
+        if dist is not None:
+            t = torch.tensor([sus_ms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sus_ms = float(t.item())
+        sustained = {"value": n * world * ksus / (sus_ms * 1e-3), "unit": UNIT, "steps": ksus, "ms_per_step": sus_ms / ksus,
+                     "device_s": sus_ms * 1e-3, "wall_s": w1, "clocks": clocks2}
+
+    # ---- policy rollout (BASELINE configs[2] style): on-device MlpPolicy inference inside every timed step, same shard
+    policy_rollout = None
+    if args.actions == "random" and args.ppo_envs_per_gpu > 0:
+        from balance_robot_b200.ppo import MlpPolicy
+        torch.manual_seed(0)
+        pol = MlpPolicy().to(dev)
+        pp = pol.pack_params()
+        o = obs_t
+        for k in range(3):
+            o = env.step(pol.act_fused(o, generator=gen, params=pp)[3])[0]
+        kp = max(10, args.steps)
+        evp = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(kp)]
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        for k in range(kp):
+            flush.fill_(k & 0xFF)
+            evp[k][0].record()
+            o = env.step(pol.act_fused(o, generator=gen, params=pp)[3])[0]
+            evp[k][1].record()
+        torch.cuda.synchronize(dev)
+        pms = sum(a.elapsed_time(b) for a, b in evp)
+        if dist is not None:
+            t = torch.tensor([pms], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            pms = float(t.item())
+        policy_rollout = {"value": n * world * kp / (pms * 1e-3), "unit": UNIT, "steps": kp, "ms_per_step": pms / kp,
+                          "policy": "MlpPolicy 6-64-64-2 tanh (random init, seed 0), sampled on the device every step (brb_policy_act: 1 launch)"}
+    env.close()
+
+    # ---- ppo: rollout + update with the gradient all-reduce at N ranks (BASELINE configs[4]: Env01-v2, 1M envs per GPU)
+    ppo_rec = ppo_sub_record(args, rank, world, dev, dist) if args.ppo_envs_per_gpu > 0 else None
+
     if rank != 0:
-        env.close()
         if dist is not None:
             dist.destroy_process_group()
         return
@@ -271,26 +339,41 @@ def run_b200(args, rank, world, local_rank):
     csub = stats1["contact_substeps"] - stats0["contact_substeps"]
     active = csub / max(1, sub)
     kernel_ms = total_ms / args.steps
-    # roofline of the dominant (only) kernel, per launch = one shard step
-    alg_flop_launch = ALG_FLOP_PER_ENV_STEP * n
-    achieved = alg_flop_launch / (kernel_ms * 1e-3) / 1e12
+    # roofline of the dominant (only) kernel, per launch = one shard step.  `achieved` / `frac` use SURVEY.md 8(d)'s preferred
+    # contact-weighted count F = 250 (1000 + 2700 active_fraction) FLOP per robot-step with the contact-active fraction measured by
+    # the kernel's own counters in this run; `executed` is what the hardware did: (2 FFMA + FMUL + FADD thread instructions of the
+    # committed ncu capture of this command) per robot-step x robots / this run's kernel time.
     occ_flop = FRAME_SKIP * (FLOP_PER_SUBSTEP_AIR + (FLOP_PER_SUBSTEP_CONTACT - FLOP_PER_SUBSTEP_AIR) * active) * n
+    achieved = occ_flop / (kernel_ms * 1e-3) / 1e12
+    all_contact = ALG_FLOP_PER_ENV_STEP * n / (kernel_ms * 1e-3) / 1e12
     try:
         peaks = json.load(open(ROOT / "MEASURED_PEAKS.json"))
     except Exception:
         peaks = {}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    ncu = load_ncu_summary()
+    executed = None
+    traffic = None
+    if ncu:
+        per_robot = (2 * ncu["thread_inst_ffma"] + ncu["thread_inst_fmul"] + ncu["thread_inst_fadd"]) / ncu["robots"]
+        executed = {"flop_per_env_step": per_robot, "achieved": per_robot * n / (kernel_ms * 1e-3) / 1e12,
+                    "frac": per_robot * n / (kernel_ms * 1e-3) / fp32_peak, "pipe_fma_pct": ncu.get("pipe_fma_pct"),
+                    "issue_active_pct": ncu.get("issue_active_pct"), "lanes_active": ncu.get("lanes_active"),
+                    "registers": ncu.get("registers"), "source": ncu["source"],
+                    "note": "counters from the committed single-launch ncu capture (same command, 65,536 robots), time from this run"}
+        traffic = ncu["dram_bytes"] / ncu["robots"] * n
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak / 1e12, "unit": "TFLOP/s",
                 "frac": achieved / (fp32_peak / 1e12),
-                "traffic": NCU_DRAM_BYTES_PER_ENV_STEP * n,
-                "traffic_source": "dram__bytes_read.sum + dram__bytes_write.sum per launch from profiles/r1_step_kernel_ncu_raw.csv "
-                                  "(213 B per robot-step, scaled to this shard); algorithmic bytes = 290 B per robot-step",
+                "formula": "250 x (1000 + 2700 x contact_active_fraction) FLOP per robot-step (SURVEY.md 8d), contact_active_fraction measured in this run",
+                "traffic": traffic,
+                "traffic_source": (f"dram__bytes_read.sum + dram__bytes_write.sum per launch from {ncu['source']}, scaled to this shard; "
+                                   "algorithmic bytes = 290 B per robot-step") if ncu else None,
                 "peak_source": "FFMA probe kernel measured in this run (brb_fp32_peak_flops); MEASURED_PEAKS.json has no FP32 entry; "
                                f"nominal {NOMINAL_FP32_TFLOPS:.1f}",
-                "algorithmic_flop_per_env_step": ALG_FLOP_PER_ENV_STEP,
                 "contact_active_fraction": active,
-                "achieved_contact_weighted": occ_flop / (kernel_ms * 1e-3) / 1e12,
-                "frac_contact_weighted": occ_flop / (kernel_ms * 1e-3) / fp32_peak,
+                "executed": executed,
+                "all_contact_count": {"flop_per_env_step": ALG_FLOP_PER_ENV_STEP, "achieved": all_contact, "frac": all_contact / (fp32_peak / 1e12),
+                                      "note": "auxiliary: charges 4 contacts to every substep, also the airborne ones; overstates the work"},
                 "hbm": {"achieved_gbs": ALG_BYTES_PER_ENV_STEP * n / (kernel_ms * 1e-3) / 1e9, "peak_gbs": hbm_peak,
                         "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
                 "kernel": "brb_step_kernel<Env01_v2>", "kernel_ms": kernel_ms}
@@ -303,15 +386,87 @@ def run_b200(args, rank, world, local_rank):
     line = {"metric": METRIC.replace(ENV_ID, args.env), "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": kernel_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "config": workload_config(args, world), "roofline": roofline, "cpu_baseline": cpu_baseline,
-            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "wall_s": wall,
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks, "wall_s": wall, "sustained": sustained,
+            "policy_rollout": policy_rollout, "ppo": ppo_rec,
             "solver": {"nonconverged_substeps": stats1["nonconverged"] - stats0["nonconverged"],
                        "unsupported_pose_steps": stats1["unsupported"] - stats0["unsupported"],
                        "solves_per_contact_substep": (stats1["solves"] - stats0["solves"]) / max(1, csub),
                        "episodes": stats1["episodes"] - stats0["episodes"]}}
     print(json.dumps(line), flush=True)
-    env.close()
     if dist is not None:
         dist.destroy_process_group()
+
+
+def ppo_sub_record(args, rank, world, dev, dist):
+    """Trained env-steps/s of on-device PPO (rollout with policy inference + update) at `world` ranks: envs sharded by rank, one
+    flat-gradient all-reduce (NCCL) per minibatch.  Device-timed, max over ranks; the update is also split into its three pieces
+    (gradient kernels / all-reduce / clip + Adam kernel), each timed alone over the same minibatch shapes."""
+    import ctypes as C
+    import torch
+    from balance_robot_b200 import make_vec, _cabi
+    from balance_robot_b200.ppo import PPO, PPOConfig
+    n = args.ppo_envs_per_gpu
+    cfg = PPOConfig(n_steps=16, n_epochs=10, n_minibatches=4, seed=0)
+    env = make_vec(args.env, n, device=dev, seed=args.seed + 7, env_id_offset=rank * n)
+    agent = PPO(env, cfg, device=dev, rank=rank, world_size=world)
+    agent.collect_rollouts(); agent.train()                   # warm-up iteration (also past the all-airborne start)
+
+    def maxr(ms):
+        if dist is None:
+            return ms
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    e = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    roll_ms = upd_ms = 0.0
+    for _ in range(args.ppo_iters):
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        e[0].record(); agent.collect_rollouts(); e[1].record(); agent.train(); e[2].record()
+        torch.cuda.synchronize(dev)
+        roll_ms += e[0].elapsed_time(e[1]); upd_ms += e[1].elapsed_time(e[2])
+    roll_ms, upd_ms = maxr(roll_ms / args.ppo_iters), maxr(upd_ms / args.ppo_iters)
+    # pieces of one minibatch update, each alone
+    total = cfg.n_steps * n
+    mb = total // cfg.n_minibatches
+    L, stream = _cabi.lib(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    b = agent.buf
+    obs, act = b["obs"].reshape(total, 6), b["actions"].reshape(total, 2)
+    oldlp, adv, ret = b["logp"].reshape(total), b["adv"].reshape(total).contiguous(), b["ret"].reshape(total).contiguous()
+    idx = torch.randperm(total, device=dev)[:mb]
+    astats = torch.tensor([0.0, 1.0], device=dev)
+    g, st = torch.zeros_like(agent._gflat), torch.zeros(4, device=dev)
+    p2, m2, v2 = agent._pflat.clone(), agent._m.clone(), agent._v.clone()
+
+    def timed(fn, reps):
+        fn(); torch.cuda.synchronize(dev)
+        a, z = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+        a.record()
+        for _ in range(reps):
+            fn()
+        z.record(); torch.cuda.synchronize(dev)
+        return maxr(a.elapsed_time(z) / reps)
+    grad_ms = timed(lambda: _cabi.check(L.brb_ppo_grad(p2.data_ptr(), obs.data_ptr(), act.data_ptr(), oldlp.data_ptr(), adv.data_ptr(), ret.data_ptr(),
+                                                       idx.data_ptr(), mb, astats.data_ptr(), cfg.clip_range, cfg.vf_coef, cfg.ent_coef,
+                                                       g.data_ptr(), st.data_ptr(), stream), "brb_ppo_grad"), 5)
+    ar_ms = timed(lambda: dist.all_reduce(g), 20) if dist is not None else 0.0
+    adam_ms = timed(lambda: _cabi.check(L.brb_adam_clip_step(p2.data_ptr(), g.data_ptr(), m2.data_ptr(), v2.data_ptr(), p2.numel(), 3e-4, 0.9, 0.999,
+                                                             1e-5, 1, 0.5, 1.0 / world, None, stream), "brb_adam_clip_step"), 20)
+    nupd = cfg.n_epochs * cfg.n_minibatches
+    out = {"value": n * world * cfg.n_steps / ((roll_ms + upd_ms) * 1e-3), "unit": "trained env-steps/s", "envs_per_gpu": n, "n_gpus": world,
+           "rollout_ms": roll_ms, "update_ms": upd_ms, "rollout_env_steps_per_s": n * world * cfg.n_steps / (roll_ms * 1e-3),
+           "update_samples_per_s": total * world * cfg.n_epochs / (upd_ms * 1e-3),
+           "update_split_ms_per_minibatch": {"grad_kernels": grad_ms, "all_reduce": ar_ms, "clip_adam_kernel": adam_ms,
+                                             "measured_whole": upd_ms / nupd},
+           "config": f"{args.env}, {n} envs per GPU, n_steps {cfg.n_steps}, {cfg.n_epochs} epochs x {cfg.n_minibatches} minibatches of {mb} samples "
+                     f"per rank, one {4 * agent._pflat.numel()} B gradient all-reduce per minibatch ({'NCCL' if world > 1 else 'single rank: none'})",
+           "iterations_timed": args.ppo_iters}
+    env.close()
+    return out
 
 
 def main():

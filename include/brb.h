@@ -141,6 +141,10 @@ int brb_fp32_peak_flops(int device, double *flops_out, double *ms_out);
 int brb_policy_act(const float *params, const float *obs, const float *noise, int64_t n, float *actions, float *actions_clipped,
                    float *values, float *logp, void *stream);
 
+/* Critic only, for the rows whose mask byte is non-zero (values of the other rows = 0): gamma * V(terminal_observation) of SB3's
+ * TimeLimit bootstrap (on_policy_algorithm.collect_rollouts, third party) without a host-side "any truncated?" test. */
+int brb_policy_value_masked(const float *params, const float *obs, const uint8_t *mask, int64_t n, float *values, void *stream);
+
 /* One PPO minibatch, forward + loss + backward fused (SB3 PPO.train() inner loop, third party; reference src/sb_rl.py:63-71
  * runs it with SB3's defaults): for the mb samples idx[0..mb) of the rollout buffer (obs [S,6], actions [S,2] unclipped,
  * old_logp / adv / returns [S])
@@ -148,9 +152,19 @@ int brb_policy_act(const float *params, const float *obs, const float *noise, in
  *   r = exp(log_prob - old_logp), A = (adv - adv_stats[0]) * adv_stats[1]   (per-minibatch normalisation: mean, 1 / (std + eps))
  * grad [BRB_POLICY_NPARAM] (parameter-block layout) and stats[4] = {policy_loss, value_loss, approx_kl, clip_fraction}
  * are ACCUMULATED: zero them before the call.  All pointers are device pointers. */
+/* Runs on the tensor cores (tcgen05.mma, bf16 hi/lo split = three passes per product, fp32 accumulation in TMEM; csrc/brb_policy_tc.cu).
+ * brb_ppo_tc_fault(device) synchronises and returns 1 if one of that kernel's bounded pipeline waits ever timed out (0 otherwise). */
+int brb_ppo_tc_fault(int device);
 int brb_ppo_grad(const float *params, const float *obs, const float *actions, const float *old_logp, const float *adv, const float *returns,
                  const int64_t *idx, int64_t mb, const float *adv_stats, float clip_range, float vf_coef, float ent_coef, float *grad,
                  float *stats, void *stream);
+
+/* One optimiser step on the flat parameter block, fused into one launch: g = grad * grad_scale (1 / world after an all-reduce
+ * sum), th.nn.utils.clip_grad_norm_(max_grad_norm) (<= 0: no clipping), torch.optim.Adam (SB3 PPO.train(): policy.optimizer.step(),
+ * third party; reference src/sb_rl.py:63-71).  m / v = Adam moments [n], step = 1-based step count, norm_out (nullable) receives
+ * the pre-clip gradient norm.  grad is zeroed on return (brb_ppo_grad accumulates).  All pointers are device pointers. */
+int brb_adam_clip_step(float *params, float *grad, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
+                       int64_t step, float max_grad_norm, float grad_scale, float *norm_out, void *stream);
 
 #ifdef __cplusplus
 }

@@ -78,7 +78,9 @@ def mirrored_free_run(env, spec, env_id, n_mirror, seed, steps, actions_of, tol=
     _, ur = ref.philox_draws(seed, env0, n_mirror, 0)
     obs = rv.reset(ur)
     o_dev = env.reset()
-    assert np.array_equal(obs, o_dev[:n_mirror]), "reset observations differ"
+    # f32 of the same fp64 expression; CUDA's and glibc's sincos / atan2 differ in the last fp64 bit now and then, and the 24-bit
+    # Philox uniforms put reset observations on f32 rounding ties often enough for that bit to show: equal to 1 f32 ulp
+    np.testing.assert_allclose(o_dev[:n_mirror], obs, rtol=2.5e-7, atol=0, err_msg="reset observations differ")
     in_sync = np.ones(n_mirror, bool)
     since = np.zeros(n_mirror, int)
     out = dict(compared=0, total=0, desync_events=0, early_desync=0, done_mismatch=0, horizons=[], max_rew_err=0.0, both_done=0)

@@ -99,10 +99,16 @@ def test_fused_policy_forward_matches_the_torch_policy():
     assert ms < 3.0
 
 
-def test_fused_ppo_gradient_matches_autograd():
+@pytest.mark.parametrize("path", ["tcgen05", "ffma"])
+def test_fused_ppo_gradient_matches_autograd(path, monkeypatch):
     """brb_ppo_grad (forward + clipped-surrogate / value loss + backward, two launches) against PyTorch autograd on the same
-    minibatch: gradient of every parameter and the four logged statistics."""
+    minibatch: gradient of every parameter and the four logged statistics.  path = tcgen05: the tensor-core kernel
+    (csrc/brb_policy_tc.cu, bf16 hi/lo x 3 passes, TMEM accumulators) — the default; ffma: the CUDA-core kernel (BRB_PPO_NO_TC)."""
     import ctypes as C
+    if path == "ffma":
+        monkeypatch.setenv("BRB_PPO_NO_TC", "1")
+    else:
+        monkeypatch.delenv("BRB_PPO_NO_TC", raising=False)
     from balance_robot_b200 import _cabi
     env = make_vec("Env01-v1", 4096, seed=2)
     cfg = PPOConfig(n_steps=8, seed=2, ent_coef=0.01)
@@ -139,7 +145,9 @@ def test_fused_ppo_gradient_matches_autograd():
                                          astats.data_ptr(), cfg.clip_range, cfg.vf_coef, cfg.ent_coef, g.data_ptr(), st.data_ptr(),
                                          C.c_void_p(torch.cuda.current_stream().cuda_stream)), "brb_ppo_grad")
     torch.cuda.synchronize()
+    assert _cabi.lib().brb_ppo_tc_fault(0) == 0              # no pipeline wait of the tcgen05 kernel timed out
     err = (g - g_ref).abs().max() / g_ref.abs().max()
+    print(f"{path}: max gradient error / max |gradient| = {float(err):.2e}")
     assert err < 2e-4, float(err)
     off = 0
     for p in pol.packed_parameters():                        # and block by block, relative to each block's own scale
@@ -148,6 +156,26 @@ def test_fused_ppo_gradient_matches_autograd():
         assert e < 1e-3, (off, float(e))
         off += k
     assert torch.allclose(st, s_ref, rtol=1e-3, atol=1e-6), (st, s_ref)
+    # throughput at a BASELINE configs[4]-sized minibatch (reported; the tensor-core path must not be slower than the FFMA one)
+    big = 1 << 20
+    bobs, bact = torch.randn((big, 6), device="cuda"), torch.randn((big, 2), device="cuda")
+    blp, badv, bret = torch.randn(big, device="cuda") * 0.1 - 2.0, torch.randn(big, device="cuda"), torch.randn(big, device="cuda")
+    bidx = torch.randperm(big, device="cuda")
+
+    def run():
+        _cabi.check(_cabi.lib().brb_ppo_grad(params.data_ptr(), bobs.data_ptr(), bact.data_ptr(), blp.data_ptr(), badv.data_ptr(), bret.data_ptr(),
+                                             bidx.data_ptr(), big, astats.data_ptr(), cfg.clip_range, cfg.vf_coef, cfg.ent_coef, g.data_ptr(),
+                                             st.data_ptr(), C.c_void_p(torch.cuda.current_stream().cuda_stream)), "brb_ppo_grad")
+    for _ in range(2):
+        run()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        run()
+    e1.record(); torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 5
+    print(f"{path}: brb_ppo_grad, 1M samples: {ms:.3f} ms ({big / ms * 1e3:.3e} samples/s)")
+    assert _cabi.lib().brb_ppo_tc_fault(0) == 0 and torch.isfinite(g).all()
     env.close()
 
 
