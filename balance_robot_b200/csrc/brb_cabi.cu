@@ -18,7 +18,7 @@ void brb_launch_step(int kind, const BrbModelConsts *c, const BrbState *S, const
 int brb_step_resident_ctas(int kind, int device);
 void brb_launch_group(long long n, const uint8_t *key, const unsigned *hist, unsigned *cursor, int *order, unsigned *hist_zero,
                       unsigned *cursor_zero, unsigned *queue_cursor, cudaStream_t stream);
-void brb_launch_reset(int kind, const BrbState *S, float *obs, const double *replay_u, cudaStream_t stream);
+void brb_launch_reset(int kind, const BrbState *S, float *obs, const double *replay_u, unsigned epoch, cudaStream_t stream);
 void brb_launch_done_rows(long long n, const uint8_t *done, const uint8_t *truncated, const float *terminal_obs, const float *ep_return,
                           const int32_t *ep_len, unsigned *block_count, unsigned *block_base, unsigned *ticket, int *n_done,
                           uint32_t *rows, cudaStream_t stream);
@@ -54,7 +54,23 @@ struct BrbEnv {
   uint32_t *d_rows;                                // [N][BRB_DONE_ROW_WORDS]
   int32_t *h_ndone;                                // pinned
   cudaStream_t host_stream;
+  // reset_all / set_state run on the caller's stream, the host-buffer step on host_stream: the next host step waits for this event
+  cudaEvent_t user_ev;
+  int user_ev_pending;
+  uint32_t reset_epoch;                            // number of reset_all calls so far: folded into the Philox block index
 };
+
+// Every entry point runs on the env's / model's device and leaves the caller's current device as it found it.
+struct DeviceGuard {
+  int prev = -1, target;
+  cudaError_t err = cudaSuccess;
+  explicit DeviceGuard(int dev) : target(dev) {
+    err = cudaGetDevice(&prev);
+    if (err == cudaSuccess && prev != dev) err = cudaSetDevice(dev);
+  }
+  ~DeviceGuard() { if (prev >= 0 && prev != target) cudaSetDevice(prev); }
+};
+#define ON_DEVICE(dev) DeviceGuard guard_(dev); CK(guard_.err)
 
 // BRB_DEBUG=1 in the environment prints the CUDA error string behind a BRB_ECUDA status
 #define CK(x) do { cudaError_t ck_ = (x); if (ck_ != cudaSuccess) { if (getenv("BRB_DEBUG")) fprintf(stderr, "[brb] %s:%d %s\n", __FILE__, __LINE__, cudaGetErrorString(ck_)); cudaGetLastError(); return BRB_ECUDA; } } while (0)
@@ -75,7 +91,7 @@ extern "C" int brb_model_create(const BrbModelConsts *consts, const double *time
   if (!consts || !time_table_host || !out || n_time < consts->max_episode_steps + 2) return BRB_EINVAL;
   if (consts->env_kind < BRB_ENV01_V1 || consts->env_kind > BRB_ENV03_V2 || consts->frame_skip < 1) return BRB_EINVAL;
   if (consts->nq < 9 || consts->nq > 16 || consts->nv < 8 || consts->nv > 14) return BRB_EINVAL;
-  CK(cudaSetDevice(device));
+  ON_DEVICE(device);
   BrbModel *m = (BrbModel *)calloc(1, sizeof(BrbModel));
   if (!m) return BRB_ENOMEM;
   m->consts = *consts;
@@ -99,7 +115,7 @@ static size_t align_up(size_t x) { return (x + 255) & ~(size_t)255; }
 
 extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64_t env_id_offset, BrbEnv **out) {
   if (!m || !out || n <= 0 || n > 0x7FFFFFFFLL) return BRB_EINVAL;      // the visit order holds 32-bit env indices
-  CK(cudaSetDevice(m->device));
+  ON_DEVICE(m->device);
   BrbEnv *e = (BrbEnv *)calloc(1, sizeof(BrbEnv));
   if (!e) return BRB_ENOMEM;
   e->model = m;
@@ -158,14 +174,16 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
   e->max_ctas = getenv("BRB_NO_QUEUE") ? 0 : brb_step_resident_ctas(m->consts.env_kind, m->device);
   if (cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaFree(e->arena); free(e); return BRB_ECUDA; }
   if (cudaMallocHost(&e->h_ndone, sizeof(int32_t)) != cudaSuccess) { cudaStreamDestroy(e->host_stream); cudaFree(e->arena); free(e); return BRB_ENOMEM; }
+  if (cudaEventCreateWithFlags(&e->user_ev, cudaEventDisableTiming) != cudaSuccess) { cudaFreeHost(e->h_ndone); cudaStreamDestroy(e->host_stream); cudaFree(e->arena); free(e); return BRB_ECUDA; }
   *out = e;
   return BRB_OK;
 }
 
 extern "C" void brb_env_destroy(BrbEnv *e) {
   if (!e) return;
-  cudaSetDevice(e->model->device);
+  DeviceGuard guard_(e->model->device);
   cudaStreamDestroy(e->host_stream);
+  cudaEventDestroy(e->user_ev);
   cudaFreeHost(e->h_ndone);
   cudaFree(e->arena);
   free(e);
@@ -202,18 +220,21 @@ static void launch_step(BrbEnv *e, const float *actions, float *obs, float *rewa
 
 extern "C" int brb_env_reset_all(BrbEnv *e, float *obs, const double *replay_u_reset, void *stream) {
   if (!e || !obs) return BRB_EINVAL;
-  CK(cudaSetDevice(e->model->device));
-  brb_launch_reset(e->model->consts.env_kind, &e->S, obs, replay_u_reset, (cudaStream_t)stream);
+  ON_DEVICE(e->model->device);
+  brb_launch_reset(e->model->consts.env_kind, &e->S, obs, replay_u_reset, e->reset_epoch, (cudaStream_t)stream);
+  e->reset_epoch++;
   e->launches++;
   e->have_order = 0;
   CK(cudaGetLastError());
+  CK(cudaEventRecord(e->user_ev, (cudaStream_t)stream));
+  e->user_ev_pending = 1;
   return BRB_OK;
 }
 
 extern "C" int brb_env_step(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,
                             float *terminal_obs, float *ep_return, int32_t *ep_len, const double *replay_u, void *stream) {
   if (!e || !actions || !obs) return BRB_EINVAL;
-  CK(cudaSetDevice(e->model->device));
+  ON_DEVICE(e->model->device);
   launch_step(e, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u, (cudaStream_t)stream);
   CK(cudaGetLastError());
   return BRB_OK;
@@ -222,9 +243,10 @@ extern "C" int brb_env_step(BrbEnv *e, const float *actions, float *obs, float *
 extern "C" int brb_env_step_host(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, uint8_t *truncated,
                                  float *terminal_obs, float *ep_return, int32_t *ep_len) {
   if (!e || !actions || !obs) return BRB_EINVAL;
-  CK(cudaSetDevice(e->model->device));
+  ON_DEVICE(e->model->device);
   const size_t N = (size_t)e->S.n;
   cudaStream_t s = e->host_stream;
+  if (e->user_ev_pending) { CK(cudaStreamWaitEvent(s, e->user_ev, 0)); e->user_ev_pending = 0; }
   CK(cudaMemcpyAsync(e->d_actions, actions, 2 * N * sizeof(float), cudaMemcpyHostToDevice, s));
   launch_step(e, e->d_actions, e->d_obs, e->d_reward, e->d_done, e->d_trunc, e->d_tobs, e->d_epret, e->d_eplen, nullptr, s);
   CK(cudaGetLastError());
@@ -242,9 +264,10 @@ extern "C" int brb_env_step_host(BrbEnv *e, const float *actions, float *obs, fl
 extern "C" int brb_env_step_host_compact(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, int32_t *n_done,
                                          uint32_t *done_rows, int64_t max_rows) {
   if (!e || !actions || !obs || !n_done || (max_rows > 0 && !done_rows) || max_rows < 0) return BRB_EINVAL;
-  CK(cudaSetDevice(e->model->device));
+  ON_DEVICE(e->model->device);
   const size_t N = (size_t)e->S.n;
   cudaStream_t s = e->host_stream;
+  if (e->user_ev_pending) { CK(cudaStreamWaitEvent(s, e->user_ev, 0)); e->user_ev_pending = 0; }
   CK(cudaMemcpyAsync(e->d_actions, actions, 2 * N * sizeof(float), cudaMemcpyHostToDevice, s));
   launch_step(e, e->d_actions, e->d_obs, e->d_reward, e->d_done, e->d_trunc, e->d_tobs, e->d_epret, e->d_eplen, nullptr, s);
   brb_launch_done_rows(e->S.n, e->d_done, e->d_trunc, e->d_tobs, e->d_epret, e->d_eplen, e->d_blk_count, e->d_blk_base, e->d_ticket,
@@ -268,7 +291,7 @@ extern "C" int brb_env_step_host_compact(BrbEnv *e, const float *actions, float 
 
 extern "C" int brb_env_get_state(BrbEnv *e, double *qpos, double *qvel, double *xquat, void *stream) {
   if (!e) return BRB_EINVAL;
-  CK(cudaSetDevice(e->model->device));
+  ON_DEVICE(e->model->device);
   brb_launch_get_state(&e->S, qpos, qvel, xquat, (cudaStream_t)stream);
   e->launches++;
   CK(cudaGetLastError());
@@ -277,16 +300,18 @@ extern "C" int brb_env_get_state(BrbEnv *e, double *qpos, double *qvel, double *
 
 extern "C" int brb_env_set_state(BrbEnv *e, const double *qpos, const double *qvel, void *stream) {
   if (!e || !qpos || !qvel) return BRB_EINVAL;
-  CK(cudaSetDevice(e->model->device));
+  ON_DEVICE(e->model->device);
   brb_launch_set_state(&e->S, qpos, qvel, (cudaStream_t)stream);
   e->launches++;
   CK(cudaGetLastError());
+  CK(cudaEventRecord(e->user_ev, (cudaStream_t)stream));
+  e->user_ev_pending = 1;
   return BRB_OK;
 }
 
 extern "C" int brb_env_get_elapsed(BrbEnv *e, int32_t *elapsed, void *stream) {
   if (!e || !elapsed) return BRB_EINVAL;
-  CK(cudaSetDevice(e->model->device));
+  ON_DEVICE(e->model->device);
   brb_launch_get_elapsed(&e->S, elapsed, (cudaStream_t)stream);
   e->launches++;
   CK(cudaGetLastError());
@@ -295,7 +320,7 @@ extern "C" int brb_env_get_elapsed(BrbEnv *e, int32_t *elapsed, void *stream) {
 
 extern "C" int brb_env_get_stats(BrbEnv *e, uint64_t out[BRB_NSTATS]) {
   if (!e || !out) return BRB_EINVAL;
-  CK(cudaSetDevice(e->model->device));
+  ON_DEVICE(e->model->device);
   CK(cudaDeviceSynchronize());
   CK(cudaMemcpy(out, e->S.stats, sizeof(uint64_t) * BRB_NSTATS, cudaMemcpyDeviceToHost));
   return BRB_OK;
@@ -303,7 +328,7 @@ extern "C" int brb_env_get_stats(BrbEnv *e, uint64_t out[BRB_NSTATS]) {
 
 extern "C" int brb_fp32_peak_flops(int device, double *flops_out, double *ms_out) {
   if (!flops_out) return BRB_EINVAL;
-  CK(cudaSetDevice(device));
+  ON_DEVICE(device);
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 4096;

@@ -1029,7 +1029,7 @@ __global__ void brb_done_rows_kernel(long long n, const uint8_t *__restrict__ do
 }
 
 template <int KIND>
-__global__ void brb_reset_kernel(const BrbState S, float *__restrict__ obs, const double *__restrict__ replay_u) {
+__global__ void brb_reset_kernel(const BrbState S, float *__restrict__ obs, const double *__restrict__ replay_u, const unsigned epoch) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S.n) return;
   S.event[i] = 0u;
@@ -1037,7 +1037,7 @@ __global__ void brb_reset_kernel(const BrbState S, float *__restrict__ obs, cons
   if (KIND == BRB_ENV03_V2) {
     double ur[32];
     if (replay_u) { for (int k = 0; k < 32; k++) ur[k] = replay_u[i * 32 + k]; }
-    else { for (int b = 0; b < 8; b++) draw4(S.seed, (uint64_t)(S.env0 + i), 0u, 1u + b, ur + 4 * b); }
+    else { for (int b = 0; b < 8; b++) draw4(S.seed, (uint64_t)(S.env0 + i), 0u, 1u + b + 16u * epoch, ur + 4 * b); }
     reset_env03(S, i, ur, o);
   } else {
     double ur[16];
@@ -1046,7 +1046,7 @@ __global__ void brb_reset_kernel(const BrbState S, float *__restrict__ obs, cons
       for (int k = 0; k < 16; k++) ur[k] = replay_u[i * 16 + k];
     } else {
 #pragma unroll
-      for (int b = 0; b < 4; b++) draw4(S.seed, (uint64_t)(S.env0 + i), 0u, 1u + b, ur + 4 * b);
+      for (int b = 0; b < 4; b++) draw4(S.seed, (uint64_t)(S.env0 + i), 0u, 1u + b + 16u * epoch, ur + 4 * b);
     }
     reset_env<KIND>(S, i, ur, o);
   }
@@ -1147,13 +1147,15 @@ extern "C" void brb_launch_done_rows(long long n, const uint8_t *done, const uin
   brb_done_rows_kernel<<<nb, 256, 0, stream>>>(n, done, truncated, terminal_obs, ep_return, ep_len, block_base, rows);
 }
 
-extern "C" void brb_launch_reset(int kind, const BrbState *S, float *obs, const double *replay_u, cudaStream_t stream) {
+// epoch = number of earlier reset_all calls on this env object: VecEnv.reset() called again draws NEW start states (block index
+// 1 + b + 16 epoch of event 0), as the reference's RNG streams keep advancing across resets; epoch 0 is what the parity tests replay
+extern "C" void brb_launch_reset(int kind, const BrbState *S, float *obs, const double *replay_u, unsigned epoch, cudaStream_t stream) {
   const unsigned grid = (unsigned)((S->n + 127) / 128);
   switch (kind) {
-    case BRB_ENV01_V1: brb_reset_kernel<BRB_ENV01_V1><<<grid, 128, 0, stream>>>(*S, obs, replay_u); break;
-    case BRB_ENV01_V2: brb_reset_kernel<BRB_ENV01_V2><<<grid, 128, 0, stream>>>(*S, obs, replay_u); break;
-    case BRB_ENV01_V3: brb_reset_kernel<BRB_ENV01_V3><<<grid, 128, 0, stream>>>(*S, obs, replay_u); break;
-    default: brb_reset_kernel<BRB_ENV03_V2><<<grid, 128, 0, stream>>>(*S, obs, replay_u); break;
+    case BRB_ENV01_V1: brb_reset_kernel<BRB_ENV01_V1><<<grid, 128, 0, stream>>>(*S, obs, replay_u, epoch); break;
+    case BRB_ENV01_V2: brb_reset_kernel<BRB_ENV01_V2><<<grid, 128, 0, stream>>>(*S, obs, replay_u, epoch); break;
+    case BRB_ENV01_V3: brb_reset_kernel<BRB_ENV01_V3><<<grid, 128, 0, stream>>>(*S, obs, replay_u, epoch); break;
+    default: brb_reset_kernel<BRB_ENV03_V2><<<grid, 128, 0, stream>>>(*S, obs, replay_u, epoch); break;
   }
 }
 

@@ -69,15 +69,17 @@ __device__ __forceinline__ bool mbar_wait(uint32_t bar, uint32_t parity) {
   }
   return false;
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
-  uint32_t r[16];
+// 16 consecutive accumulator columns of this thread's TMEM lane -> v[0..15]; asynchronous: tmem_ld_wait() before v is used
+__device__ __forceinline__ void tmem_ld16_async(uint32_t taddr, float *v) {
   asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
-                 "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "=f"(v[0]), "=f"(v[1]), "=f"(v[2]), "=f"(v[3]), "=f"(v[4]), "=f"(v[5]), "=f"(v[6]), "=f"(v[7]), "=f"(v[8]), "=f"(v[9]),
+                 "=f"(v[10]), "=f"(v[11]), "=f"(v[12]), "=f"(v[13]), "=f"(v[14]), "=f"(v[15])
                : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-  for (int k = 0; k < 16; k++) v[k] = __uint_as_float(r[k]);
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+  tmem_ld16_async(taddr, v);
+  tmem_ld_wait();
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   uint32_t r[8];
@@ -209,15 +211,33 @@ __global__ void __launch_bounds__(128, 2) brb_ppo_grad_tc_kernel(const float *__
   bool first_tile = true, pending = false, ok = true;
 
   const long long ntiles = (mb + 127) / 128;
+  // sample data is gathered through idx (random rows of the rollout buffer): every gather is issued one phase ahead of its use, so
+  // that its latency hides behind an MMA wait (with two warps per scheduler nothing else would cover it: ncu long_scoreboard 2.1)
+  long long i_next = 0;
+  float x_next[PIN];
+  {
+    const long long s0 = (long long)blockIdx.x * 128 + tid;
+    i_next = idx[s0 < mb ? s0 : 0];
+#pragma unroll
+    for (int k = 0; k < PIN; k++) x_next[k] = obs[i_next * PIN + k];
+  }
   for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const long long s = tile * 128 + tid;
     const bool valid = s < mb;
-    const long long i = idx[valid ? s : 0];
+    const long long i = i_next;
     // ---- P1: first layer on the CUDA cores, H1 -> buffer A, [x | 1 | 0] -> X
     float x[8];
 #pragma unroll
-    for (int k = 0; k < PIN; k++) x[k] = obs[i * PIN + k];
+    for (int k = 0; k < PIN; k++) x[k] = x_next[k];
     x[6] = 1.f; x[7] = 0.f;
+    {   // next tile's row index (its observation is fetched during P3)
+      const long long sn = (tile + gridDim.x) * 128 + tid;
+      i_next = idx[sn < mb ? sn : 0];
+    }
+    // this tile's loss inputs, used in P2
+    float a_act[2] = {0.f, 0.f}, a_oldlp = 0.f, a_adv = 0.f, a_ret = 0.f;
+    if (ACTOR) { a_act[0] = act[i * 2]; a_act[1] = act[i * 2 + 1]; a_oldlp = oldlogp[i]; a_adv = adv[i]; }
+    else a_ret = ret[i];
     if (pending) { ok &= mbar_wait(bar, parity); parity ^= 1u; asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); pending = false; }   // M4 of the previous tile read A and X
 #pragma unroll
     for (int fb = 0; fb < 8; fb++) {
@@ -245,16 +265,14 @@ __global__ void __launch_bounds__(128, 2) brb_ppo_grad_tc_kernel(const float *__
 #pragma unroll
     for (int o = 0; o < NOUT; o++) out[o] = b3[o];
 #pragma unroll
-    for (int c = 0; c < PH; c += 16) {
-      float z[16];
-      tmem_ld16(tlane + C_Z2 + c, z);
+    for (int c = 0; c < PH; c += 16) tmem_ld16_async(tlane + C_Z2 + c, h2 + c);      // the whole accumulator row in flight, one wait
+    tmem_ld_wait();
 #pragma unroll
-      for (int q = 0; q < 16; q++) {
-        const float h = tanh_fast(z[q] + B2[c + q]);
-        h2[c + q] = h;
+    for (int j = 0; j < PH; j++) {
+      const float h = tanh_fast(h2[j] + B2[j]);
+      h2[j] = h;
 #pragma unroll
-        for (int o = 0; o < NOUT; o++) out[o] = fmaf(W3[o * PH + c + q], h, out[o]);
-      }
+      for (int o = 0; o < NOUT; o++) out[o] = fmaf(W3[o * PH + j], h, out[o]);
     }
     {
       const float m = valid ? inv_mb : 0.f;
@@ -262,11 +280,11 @@ __global__ void __launch_bounds__(128, 2) brb_ppo_grad_tc_kernel(const float *__
         float d[2], lp = 0.f;
 #pragma unroll
         for (int k = 0; k < 2; k++) {
-          d[k] = act[i * 2 + k] - out[k];
+          d[k] = a_act[k] - out[k];
           lp += -(d[k] * d[k]) * (0.5f * ivar[k]) - ls[k] - 0.91893853320467274f;
         }
-        const float lr = lp - oldlogp[i], ratio = expf(lr);
-        const float an = (adv[i] - amean) * arstd;
+        const float lr = lp - a_oldlp, ratio = expf(lr);
+        const float an = (a_adv - amean) * arstd;
         const float s1 = an * ratio, s2 = an * fminf(1.f + clip, fmaxf(1.f - clip, ratio));
         const bool inside = ratio >= 1.f - clip && ratio <= 1.f + clip;
         const float g = (inside || s1 < s2) ? -an * ratio * m : 0.f;
@@ -280,7 +298,7 @@ __global__ void __launch_bounds__(128, 2) brb_ppo_grad_tc_kernel(const float *__
         st1 += ((ratio - 1.f) - lr) * m;
         st2 += (fabsf(ratio - 1.f) > clip ? 1.f : 0.f) * m;
       } else {
-        const float diff = out[0] - ret[i];
+        const float diff = out[0] - a_ret;
         dout[0] = vf_coef * 2.f * diff * m;
         gb3[0] += dout[0];
         st0 += diff * diff * m;
@@ -301,6 +319,8 @@ __global__ void __launch_bounds__(128, 2) brb_ppo_grad_tc_kernel(const float *__
     // ---- P3: dz2 = (W3' dout)(1 - h2^2), over H2 once M2 has read it
 #pragma unroll
     for (int j = 0; j < PH; j++) h2[j] = fmaf(W3[PH + j], dout[1], W3[j] * dout[0]) * (1.f - h2[j] * h2[j]);
+#pragma unroll
+    for (int k = 0; k < PIN; k++) x_next[k] = obs[i_next * PIN + k];      // next tile's observation: in flight across the M2 / M3 waits
     ok &= mbar_wait(bar, parity); parity ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 #pragma unroll
@@ -316,17 +336,18 @@ __global__ void __launch_bounds__(128, 2) brb_ppo_grad_tc_kernel(const float *__
     // ---- P4: dz1 = dh1 (1 - h1^2) in place over H1
     ok &= mbar_wait(bar, parity); parity ^= 1u;
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    {
+      float *dh = h2;                                                               // same registers: dz2 is in shared memory now
 #pragma unroll
-    for (int c = 0; c < PH; c += 16) {
-      float dh[16];
-      tmem_ld16(tlane + C_DH1 + c, dh);
+      for (int c = 0; c < PH; c += 16) tmem_ld16_async(tlane + C_DH1 + c, dh + c);
+      tmem_ld_wait();
 #pragma unroll
-      for (int half = 0; half < 2; half++) {
+      for (int fb = 0; fb < 8; fb++) {
         float h1[8];
-        load8(AH, AL, A_FB, tid, (c >> 3) + half, h1);
+        load8(AH, AL, A_FB, tid, fb, h1);
 #pragma unroll
-        for (int q = 0; q < 8; q++) h1[q] = dh[8 * half + q] * (1.f - h1[q] * h1[q]);
-        store8(AH, AL, A_FB, tid, (c >> 3) + half, h1);
+        for (int q = 0; q < 8; q++) h1[q] = dh[8 * fb + q] * (1.f - h1[q] * h1[q]);
+        store8(AH, AL, A_FB, tid, fb, h1);
       }
     }
     publish_to_mma();

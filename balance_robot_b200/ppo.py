@@ -11,7 +11,9 @@ rollout / batch sizes that scale with the number of envs (SB3's 2048 x 1 env is 
 
 Multi-GPU: one process per GPU (torchrun), envs sharded by rank; the only collectives are one flat-gradient
 all-reduce per minibatch and one all-reduce of the rollout statistics (NCCL over NVLink; gloo in CPU tests).
-The policy state-dict uses SB3's key names so checkpoints can be exchanged with the reference tooling.
+Checkpoints are written in Stable-Baselines3's model.zip layout (sb3_format.py: `data` with SB3's attribute names, the
+policy class and the Box spaces as version-independent pickle streams, SB3's state-dict key names); zips written by SB3's
+PPO("MlpPolicy") load here.  Loading OUR zips into real SB3 could not be run in this image (SB3 is not installable).
 """
 from __future__ import annotations
 
@@ -401,6 +403,7 @@ class PPO:
             roll = self.collect_rollouts()
             upd = self.train()
             it += 1
+            self._check_unsupported_poses()
             fps = self.num_timesteps / max(1e-9, time.time() - t0)
             rec = dict(roll, **upd, fps=fps, total_timesteps=self.num_timesteps, iterations=it)
             if self.rank == 0:
@@ -417,39 +420,64 @@ class PPO:
                 break
         return self
 
-    # ---- checkpoints: zip laid out like SB3's (data / policy.pth / policy.optimizer.pth / pytorch_variables.pth)
+    def _check_unsupported_poses(self) -> None:
+        """The step kernels count env-steps that ended in a pose whose contacts they do not model (chassis on the floor, a
+        wheel lying flat): those transitions are simulated without that contact.  Unreachable before the 50 degree
+        termination in Env01 (0 in every soak so far), but a trainer must not consume them silently."""
+        stats = getattr(self.env, "stats", None)
+        if stats is None:
+            return
+        u = int(stats().get("unsupported", 0))
+        if u > getattr(self, "_unsupported_seen", 0):
+            import warnings
+            warnings.warn(f"{u - getattr(self, '_unsupported_seen', 0)} env-steps ended in a pose with unmodelled contacts "
+                          f"(chassis-floor / wheel lying flat; {u} in total): those transitions lack that contact force", RuntimeWarning)
+            self._unsupported_seen = u
+
+    # ---- checkpoints: Stable-Baselines3's model.zip (sb3_format.py: data / policy.pth / policy.optimizer.pth / ...)
     def save(self, path) -> pathlib.Path:
+        from . import sb3_format
         path = pathlib.Path(path)
         if path.suffix != ".zip":
             path = path.with_suffix(".zip")
         path.parent.mkdir(parents=True, exist_ok=True)
-        data = {"policy_class": "MlpPolicy", "algo": "PPO", "num_timesteps": self.num_timesteps,
-                "hyper_parameters": dataclasses.asdict(self.cfg), "observation_dim": 6, "action_dim": 2,
-                "format": "balance_robot_b200 (SB3-layout zip; state-dict keys follow SB3's ActorCriticPolicy)"}
+        n_envs = int(getattr(self.env, "num_envs", 1)) * self.world
+        osp, asp = getattr(self.env, "observation_space", None), getattr(self.env, "action_space", None)
+        obs_low, obs_high = (osp.low.tolist(), osp.high.tolist()) if osp is not None else ([-1.0] * 6, [1.0] * 6)
+        act_low, act_high = (asp.low.tolist(), asp.high.tolist()) if asp is not None else ([-1.0] * 2, [1.0] * 2)
+        batch = max(1, self.cfg.n_steps * n_envs // self.cfg.n_minibatches)
+        data = sb3_format.build_data(self.cfg, self.num_timesteps, n_envs, self._adam_t or 0, obs_low, obs_high, act_low, act_high, batch)
 
         def blob(obj):
             bio = io.BytesIO()
             torch.save(obj, bio)
             return bio.getvalue()
         self._export_adam_state()
+        # SB3 orders the optimizer's params like policy.parameters(); ours is the same module tree, so the state dict lines up
         with zipfile.ZipFile(path, "w") as z:
-            z.writestr("data", json.dumps(data, indent=1))
-            z.writestr("policy.pth", blob({k: v.detach().cpu() for k, v in self.policy.state_dict().items()}))
-            z.writestr("policy.optimizer.pth", blob(self.optimizer.state_dict()))
+            z.writestr("data", data)
             z.writestr("pytorch_variables.pth", blob(None))
-            z.writestr("_stable_baselines3_version", "balance_robot_b200-1.0")
+            z.writestr("policy.pth", blob({k: v.detach().cpu().clone() for k, v in self.policy.state_dict().items()}))
+            z.writestr("policy.optimizer.pth", blob(self.optimizer.state_dict()))
+            z.writestr("_stable_baselines3_version", sb3_format.SB3_VERSION)
+            z.writestr("system_info.txt", sb3_format.SYSTEM_INFO)
         return path
 
     @classmethod
     def load(cls, path, env, config: Optional[PPOConfig] = None, **kw) -> "PPO":
+        """Loads a model.zip written by this package or by Stable-Baselines3's PPO("MlpPolicy") with the default 64-64 tanh
+        architecture (algorithm_class.load(model_file, env=env), reference sb_rl.py:519-525)."""
+        from . import sb3_format
         path = pathlib.Path(path)
         if not path.exists():
             raise RuntimeError(f"model file {path} does not exist")        # mirrors sb_rl.py:100-101
         with zipfile.ZipFile(path) as z:
-            data = json.loads(z.read("data"))
-            sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu")
-            opt = torch.load(io.BytesIO(z.read("policy.optimizer.pth")), map_location="cpu") if "policy.optimizer.pth" in z.namelist() else None
-        cfg = config or PPOConfig(**{k: v for k, v in data.get("hyper_parameters", {}).items() if k in PPOConfig.__dataclass_fields__})
+            data = sb3_format.parse_data(z.read("data").decode())
+            sd = torch.load(io.BytesIO(z.read("policy.pth")), map_location="cpu", weights_only=False)
+            opt = (torch.load(io.BytesIO(z.read("policy.optimizer.pth")), map_location="cpu", weights_only=False)
+                   if "policy.optimizer.pth" in z.namelist() else None)
+        fields = sb3_format.ppo_config_fields(data)
+        cfg = config or PPOConfig(**{k: v for k, v in fields.items() if k in PPOConfig.__dataclass_fields__})
         self = cls(env, cfg, **kw)
         self.policy.load_state_dict(sd)
         if opt:

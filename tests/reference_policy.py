@@ -104,3 +104,25 @@ class RobotMovePolicy:
                 val[o] = lut[val[x] + 128]
         q = val[self.out]
         return (float(self.out_scale) * (q - self.out_zero).to(torch.float32)).to(torch.float32)
+
+
+def dequantised_layers(z=None):
+    """[(W, b)] of the three FULLY_CONNECTED layers on the action path as float arrays (weight = int8 x per-channel scale,
+    bias = int32 x its scale): the fp32 policy the int8 graph was quantised from, up to the rounding of the weights."""
+    z = np.load(FIXTURE) if z is None else z
+    pol = RobotMovePolicy()
+    out = []
+    ops = [(int(z[f"op{k}_code"]), [int(v) for v in z[f"op{k}_in"]], [int(v) for v in z[f"op{k}_out"]]) for k in range(int(z["n_ops"]))]
+    need, keep = {pol.out}, []
+    for code, ins, outs in reversed(ops):
+        if need & set(outs):
+            keep.append((code, ins, outs))
+            need |= {t for t in ins if f"t{t}_data" not in z}
+    for code, ins, outs in reversed(keep):
+        if code == OP_FULLY_CONNECTED:
+            x, w, b = ins
+            W = z[f"t{w}_data"].astype(np.float64) * np.broadcast_to(z[f"t{w}_scale"].astype(np.float64), (z[f"t{w}_data"].shape[0],))[:, None]
+            B = z[f"t{b}_data"].astype(np.float64) * np.broadcast_to(z[f"t{b}_scale"].astype(np.float64), z[f"t{b}_data"].shape)
+            out.append((W, B))
+    assert len(out) == 3
+    return out

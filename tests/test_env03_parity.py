@@ -7,6 +7,7 @@ import numpy as np
 import pytest
 
 import helpers
+import parity_checks as pc
 from balance_robot_b200 import mjcf, model
 from oracle import ref
 
@@ -26,7 +27,7 @@ def env03_single_step(env, rv, n, seed, steps):
     _, ur = ref.env03_draws(seed, 0, n, 0)
     obs = rv.reset(ur)
     o_dev = env.reset()
-    assert np.array_equal(obs, o_dev)
+    pc.assert_f32_equal(o_dev, obs, 1)
     rng = np.random.default_rng(seed)
     er, eb, impacts = [], [], 0
     chk = dict(steps=0, done_mismatch=0, max_rew_err=0.0, max_obs_err=0.0, refired=0, parked=0)
