@@ -195,8 +195,11 @@ class PPO:
         self.fused_update = True      # CUDA: minibatch forward + loss + backward through brb_ppo_grad (False: autograd)
         self._gflat = self._pflat = None
         self._adam_t = 0
+        self._comm = None
         if self.device.type == "cuda" and self.policy.action_net.in_features == 64:
             self._flatten_parameters()
+            if world_size > 1:
+                self._setup_peer_comm()
         self._obs = None
         self.ep_stats = {"return_sum": 0.0, "len_sum": 0.0, "count": 0.0}
         n, T = env.num_envs, config.n_steps
@@ -223,6 +226,43 @@ class PPO:
             p.data = flat[off:off + k].view_as(p)
             p.grad = self._gflat[off:off + k].view_as(p)
             off += k
+
+    def _setup_peer_comm(self) -> None:
+        """Peer-memory block for the fused all-reduce + clip + Adam kernel (csrc/brb_policy.cu: brb_comm_*): every rank exports its
+        block's cudaIpc handle, the handles are all-gathered through torch.distributed, every rank maps its peers' blocks.
+        Falls back to the NCCL all-reduce (+ brb_adam_clip_step) if any rank cannot map a peer, or with BRB_PPO_NO_P2P=1."""
+        import ctypes as C
+        import os
+        import torch.distributed as dist
+        from . import _cabi
+        if os.environ.get("BRB_PPO_NO_P2P") or not dist.is_initialized() or self.world > 8:
+            return
+        L = _cabi.lib()
+        comm = C.c_void_p()
+        dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
+        rc = L.brb_comm_create(self.rank, self.world, dev_index, self._pflat.numel(), C.byref(comm))
+        handle = (C.c_ubyte * 64)()
+        if rc == 0:
+            rc = L.brb_comm_export(comm, handle)
+        mine = torch.tensor(list(bytes(handle)) + [1 if rc == 0 else 0], dtype=torch.uint8, device=self.device)
+        gathered = [torch.zeros_like(mine) for _ in range(self.world)]
+        dist.all_gather(gathered, mine)
+        rows = [bytes(g.cpu().tolist()) for g in gathered]
+        ok = all(r[64] == 1 for r in rows)
+        if ok:
+            ok = L.brb_comm_open(comm, b"".join(r[:64] for r in rows)) == 0
+        flag = torch.tensor([1.0 if ok else 0.0], device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        if float(flag.item()) == 1.0:
+            self._comm = comm
+        elif comm:
+            L.brb_comm_destroy(comm)
+
+    def close(self) -> None:
+        if self._comm is not None:
+            from . import _cabi
+            _cabi.lib().brb_comm_destroy(self._comm)
+            self._comm = None
 
     def _export_adam_state(self) -> None:
         """flat Adam moments -> the torch optimizer's per-parameter state (for checkpoints in SB3's layout)."""
@@ -348,15 +388,22 @@ class PPO:
                 else:
                     astats = unit
                 with torch.cuda.device(self.device):
+                    self._adam_t += 1
+                    gptr = L.brb_comm_grad(self._comm, self._adam_t) if self._comm is not None else self._gflat.data_ptr()
                     _cabi.check(L.brb_ppo_grad(self._pflat.data_ptr(), obs.data_ptr(), act.data_ptr(), oldlp.data_ptr(), adv.data_ptr(),
                                                ret.data_ptr(), idx.data_ptr(), mb, astats.data_ptr(), cfg.clip_range, cfg.vf_coef,
-                                               cfg.ent_coef, self._gflat.data_ptr(), self._gstats.data_ptr(), stream), "brb_ppo_grad")
-                    if self.world > 1:
-                        self._all_reduce_(self._gflat)
-                    self._adam_t += 1
-                    _cabi.check(L.brb_adam_clip_step(self._pflat.data_ptr(), self._gflat.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
-                                                     self._pflat.numel(), lr, b1, b2, eps, self._adam_t, cfg.max_grad_norm or 0.0,
-                                                     1.0 / self.world, self._gnorm.data_ptr(), stream), "brb_adam_clip_step")
+                                               cfg.ent_coef, gptr, self._gstats.data_ptr(), stream), "brb_ppo_grad")
+                    if self._comm is not None:
+                        # all-reduce over NVLink peer memory + clipping + Adam: one launch on this stream, no NCCL call
+                        _cabi.check(L.brb_comm_allreduce_adam(self._comm, self._pflat.data_ptr(), self._m.data_ptr(), self._v.data_ptr(), lr, b1, b2,
+                                                              eps, self._adam_t, cfg.max_grad_norm or 0.0, self._gnorm.data_ptr(), stream),
+                                    "brb_comm_allreduce_adam")
+                    else:
+                        if self.world > 1:
+                            self._all_reduce_(self._gflat)
+                        _cabi.check(L.brb_adam_clip_step(self._pflat.data_ptr(), self._gflat.data_ptr(), self._m.data_ptr(), self._v.data_ptr(),
+                                                         self._pflat.numel(), lr, b1, b2, eps, self._adam_t, cfg.max_grad_norm or 0.0,
+                                                         1.0 / self.world, self._gnorm.data_ptr(), stream), "brb_adam_clip_step")
                 updates += 1
         vals = (self._gstats / max(1, updates)).tolist()
         return dict(zip(("policy_loss", "value_loss", "approx_kl", "clip_fraction"), vals))

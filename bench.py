@@ -453,18 +453,32 @@ def ppo_sub_record(args, rank, world, dev, dist):
     grad_ms = timed(lambda: _cabi.check(L.brb_ppo_grad(p2.data_ptr(), obs.data_ptr(), act.data_ptr(), oldlp.data_ptr(), adv.data_ptr(), ret.data_ptr(),
                                                        idx.data_ptr(), mb, astats.data_ptr(), cfg.clip_range, cfg.vf_coef, cfg.ent_coef,
                                                        g.data_ptr(), st.data_ptr(), stream), "brb_ppo_grad"), 5)
-    ar_ms = timed(lambda: dist.all_reduce(g), 20) if dist is not None else 0.0
-    adam_ms = timed(lambda: _cabi.check(L.brb_adam_clip_step(p2.data_ptr(), g.data_ptr(), m2.data_ptr(), v2.data_ptr(), p2.numel(), 3e-4, 0.9, 0.999,
-                                                             1e-5, 1, 0.5, 1.0 / world, None, stream), "brb_adam_clip_step"), 20)
+    split = {"grad_kernels": grad_ms}
+    if agent._comm is not None:
+        # the fused peer-memory kernel (all-reduce over NVLink + clipping + Adam): every rank calls it in lockstep with the next step numbers
+        def fused():
+            agent._adam_t += 1
+            _cabi.check(L.brb_comm_allreduce_adam(agent._comm, p2.data_ptr(), m2.data_ptr(), v2.data_ptr(), 3e-4, 0.9, 0.999, 1e-5, agent._adam_t,
+                                                  0.5, None, stream), "brb_comm_allreduce_adam")
+        split["allreduce_clip_adam_kernel"] = timed(fused, 20)
+        split["path"] = "one kernel: P2P loads of every rank's gradient over NVLink, clipping, Adam (brb_comm_allreduce_adam)"
+        assert L.brb_comm_fault(agent._comm) == 0
+    else:
+        split["all_reduce"] = timed(lambda: dist.all_reduce(g), 20) if dist is not None else 0.0
+        split["clip_adam_kernel"] = timed(lambda: _cabi.check(L.brb_adam_clip_step(p2.data_ptr(), g.data_ptr(), m2.data_ptr(), v2.data_ptr(), p2.numel(),
+                                                                                   3e-4, 0.9, 0.999, 1e-5, 1, 0.5, 1.0 / world, None, stream),
+                                                              "brb_adam_clip_step"), 20)
+        split["path"] = "NCCL all_reduce + brb_adam_clip_step" if dist is not None else "single rank: brb_adam_clip_step"
     nupd = cfg.n_epochs * cfg.n_minibatches
     out = {"value": n * world * cfg.n_steps / ((roll_ms + upd_ms) * 1e-3), "unit": "trained env-steps/s", "envs_per_gpu": n, "n_gpus": world,
            "rollout_ms": roll_ms, "update_ms": upd_ms, "rollout_env_steps_per_s": n * world * cfg.n_steps / (roll_ms * 1e-3),
            "update_samples_per_s": total * world * cfg.n_epochs / (upd_ms * 1e-3),
-           "update_split_ms_per_minibatch": {"grad_kernels": grad_ms, "all_reduce": ar_ms, "clip_adam_kernel": adam_ms,
-                                             "measured_whole": upd_ms / nupd},
+           "update_split_ms_per_minibatch": dict(split, measured_whole=upd_ms / nupd),
+           "grad_kernel": "brb_ppo_grad_tc_kernel: tcgen05.mma kind::f16, bf16 hi/lo split x 3 passes, fp32 accumulators in TMEM",
            "config": f"{args.env}, {n} envs per GPU, n_steps {cfg.n_steps}, {cfg.n_epochs} epochs x {cfg.n_minibatches} minibatches of {mb} samples "
                      f"per rank, one {4 * agent._pflat.numel()} B gradient all-reduce per minibatch ({'NCCL' if world > 1 else 'single rank: none'})",
            "iterations_timed": args.ppo_iters}
+    agent.close()
     env.close()
     return out
 

@@ -166,6 +166,22 @@ int brb_ppo_grad(const float *params, const float *obs, const float *actions, co
 int brb_adam_clip_step(float *params, float *grad, float *m, float *v, int64_t n, float lr, float beta1, float beta2, float eps,
                        int64_t step, float max_grad_norm, float grad_scale, float *norm_out, void *stream);
 
+/* Data-parallel PPO across the GPUs of one node, one process per GPU: the gradient all-reduce (mean over ranks), clipping and Adam
+ * as ONE kernel over NVLink peer memory (csrc/brb_policy.cu).  Every rank creates a comm object (a small symmetric block in its own
+ * HBM), exports its 64-byte cudaIpc handle, the host side all-gathers the handles (torch.distributed), every rank opens its peers'.
+ * Per optimiser step `step` (1-based, the same on every rank): brb_ppo_grad accumulates into brb_comm_grad(c, step) (zero on entry),
+ * then brb_comm_allreduce_adam on the same stream.  Sums are formed in rank order on every rank: the replicas stay bit-identical.
+ * brb_comm_fault: 1 if a (bounded) wait for a peer ever timed out.  world <= 8, n <= 10,240. */
+typedef struct BrbComm BrbComm;
+int brb_comm_create(int rank, int world, int device, int64_t n, BrbComm **out);
+int brb_comm_export(BrbComm *c, void *handle64);
+int brb_comm_open(BrbComm *c, const void *handles /* world x 64 bytes, rank order */);
+void brb_comm_destroy(BrbComm *c);
+float *brb_comm_grad(BrbComm *c, int64_t step);
+int brb_comm_fault(BrbComm *c);
+int brb_comm_allreduce_adam(BrbComm *c, float *params, float *m, float *v, float lr, float beta1, float beta2, float eps, int64_t step,
+                            float max_grad_norm, float *norm_out, void *stream);
+
 #ifdef __cplusplus
 }
 #endif
