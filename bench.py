@@ -476,7 +476,7 @@ def ppo_sub_record(args, rank, world, dev, dist):
            "update_split_ms_per_minibatch": dict(split, measured_whole=upd_ms / nupd),
            "grad_kernel": "brb_ppo_grad_tc_kernel: tcgen05.mma kind::f16, bf16 hi/lo split x 3 passes, fp32 accumulators in TMEM",
            "config": f"{args.env}, {n} envs per GPU, n_steps {cfg.n_steps}, {cfg.n_epochs} epochs x {cfg.n_minibatches} minibatches of {mb} samples "
-                     f"per rank, one {4 * agent._pflat.numel()} B gradient all-reduce per minibatch ({'NCCL' if world > 1 else 'single rank: none'})",
+                     f"per rank, one {4 * agent._pflat.numel()} B gradient all-reduce per minibatch ({split["path"]})",
            "iterations_timed": args.ppo_iters}
     agent.close()
     env.close()
