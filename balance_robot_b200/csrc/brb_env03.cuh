@@ -864,6 +864,10 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
     }
     st.bits = S.aset[i];
     st.n_contact = st.n_solve = st.n_nonconv = st.n_slots = 0;
+    for (int ci = 0; ci < 4; ci++) {     // wheel-rim contact records are read branch-free: finite values from the start
+      st.cD[ci] = 0.f;
+      for (int k = 0; k < 3; k++) st.cr[ci][k] = st.cw[ci][k] = st.cy[ci][k] = 0.f;
+    }
     nn = 0;
     for (int k = 0; k < 4; k++) { qn[k] = S.qpos[(12 + k) * N + i]; nn += qn[k] * qn[k]; }
     nn = 1.0 / sqrt(nn);

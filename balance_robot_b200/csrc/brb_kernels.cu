@@ -214,6 +214,9 @@ BRB_D void reset_env(const BrbState &S, long long i, const double u[16], float o
 // registers (a run-time contact index sends H[] to local memory — measured in profiles/r1a).
 #define LT(i, j) ((i) * ((i) + 1) / 2 + (j))   // packed lower-triangular index
 
+#ifdef BRB_TIMELINE
+__device__ unsigned long long g_timeline[1 + 4 * 65536];   // debug: per warp-task records of the step kernel
+#endif
 #ifdef BRB_TRIPSTATS
 __device__ unsigned long long g_trip[48 + 32 * 4 + 16 + 2];  // debug: warp-trips, lane-trips, warp-trips with a solve, lanes solving; [8+k]: trips with k lanes in contact; [48+4*key+cls]: robots by incoming group key and contact class of the step
 #endif
@@ -288,36 +291,38 @@ BRB_D RimDist rim_dist_fp64(const BrbModelConsts &c, const KF (&q)[4], const KF 
   return r;
 }
 
+// One rim end (slot CI = 2*wheel + end).  Branch-free on purpose: the four slots are independent dependency chains that the
+// scheduler interleaves; with one divergent region per slot the kernel ran 13 % slower although it executed fewer
+// instructions (a warp is latency-bound here: profiles/README.md, round 2).  A slot that is not in contact gets finite
+// values that nothing reads: its row pattern is forced to 0 (all-zero weights) in phys_assemble / phys_active_set.
 template <int CI, bool VI>
 BRB_D void contact_setup(const BrbModelConsts &c, Phys &P, float dist, float sa, const float (&G)[3], const float (&A)[3],
                          const float (&B2)[3], const float (&ww)[3]) {
   constexpr int k = CI >> 1, e = CI & 1;
   const float sg = k ? 1.f : -1.f;
-  if (dist < 0.f) {
-    P.valid |= 1u << CI;
-    const float hd = 0.5f * dist;
-    const float cx = sg * c.ox + (e ? -sa : sa) * c.hl;
-    // r_w = R (off_k +- a*hl + v) - e_z dist/2 ; w_w = R [axis_k x (r_b - off_k)] = sg (A + hd B2)
-    const float rx = P.ex[0] * cx + G[0], ry = P.ex[1] * cx + G[1], rz = P.ex[2] * cx + G[2] - hd;
-    const float wx = sg * (A[0] + hd * B2[0]), wy = sg * (A[1] + hd * B2[1]), wz = sg * (A[2] + hd * B2[2]);
-    const float sk = P.s[k].s;
-    // material-point velocity in the world frame: v + w_w x r_w + s_k w_w
-    const float px = P.v[0].s + ww[1] * rz - ww[2] * ry + sk * wx;
-    const float py = P.v[1].s + ww[2] * rx - ww[0] * rz + sk * wy;
-    const float pz = P.v[2].s + ww[0] * ry - ww[1] * rx + sk * wz;
-    P.cr[CI][0] = rx; P.cr[CI][1] = ry; P.cr[CI][2] = rz;
-    P.cw[CI][0] = wx; P.cw[CI][1] = wy; P.cw[CI][2] = wz;
-    if (VI) {
-      const float imp = imp_of(c.pp[0], dist);
-      P.cD[CI] = __fdividef(c.pp[0][3] * imp, 1.f - imp);
-      P.cy[CI][0] = c.pp[0][2] * pz + c.pp[0][1] * imp * dist;
-      P.cy[CI][1] = c.pp[0][2] * py;
-      P.cy[CI][2] = -c.pp[0][2] * px;
-    } else {
-      P.cy[CI][0] = c.Bdamp * pz + c.Kimp * dist;
-      P.cy[CI][1] = c.Bdamp * py;
-      P.cy[CI][2] = -c.Bdamp * px;
-    }
+  P.valid |= (dist < 0.f) ? (1u << CI) : 0u;
+  const float hd = 0.5f * dist;
+  const float cx = sg * c.ox + (e ? -sa : sa) * c.hl;
+  // r_w = R (off_k +- a*hl + v) - e_z dist/2 ; w_w = R [axis_k x (r_b - off_k)] = sg (A + hd B2)
+  const float rx = P.ex[0] * cx + G[0], ry = P.ex[1] * cx + G[1], rz = P.ex[2] * cx + G[2] - hd;
+  const float wx = sg * (A[0] + hd * B2[0]), wy = sg * (A[1] + hd * B2[1]), wz = sg * (A[2] + hd * B2[2]);
+  const float sk = P.s[k].s;
+  // material-point velocity in the world frame: v + w_w x r_w + s_k w_w
+  const float px = P.v[0].s + ww[1] * rz - ww[2] * ry + sk * wx;
+  const float py = P.v[1].s + ww[2] * rx - ww[0] * rz + sk * wy;
+  const float pz = P.v[2].s + ww[0] * ry - ww[1] * rx + sk * wz;
+  P.cr[CI][0] = rx; P.cr[CI][1] = ry; P.cr[CI][2] = rz;
+  P.cw[CI][0] = wx; P.cw[CI][1] = wy; P.cw[CI][2] = wz;
+  if (VI) {
+    const float imp = imp_of(c.pp[0], dist);
+    P.cD[CI] = __fdividef(c.pp[0][3] * imp, 1.f - imp);
+    P.cy[CI][0] = c.pp[0][2] * pz + c.pp[0][1] * imp * dist;
+    P.cy[CI][1] = c.pp[0][2] * py;
+    P.cy[CI][2] = -c.pp[0][2] * px;
+  } else {
+    P.cy[CI][0] = c.Bdamp * pz + c.Kimp * dist;
+    P.cy[CI][1] = c.Bdamp * py;
+    P.cy[CI][2] = -c.Bdamp * px;
   }
 }
 
@@ -390,7 +395,6 @@ BRB_D void phys_setup(const BrbModelConsts &c, Phys &P) {
 // force to O(D*eps) ~ 2e-5 N, and without the hysteresis fp32 noise can flip such a row back and forth forever.
 template <int CI>
 BRB_D unsigned contact_bits(const BrbModelConsts &c, const Phys &P, const float (&a)[8], unsigned prev, float mu, float eps) {
-  if (!(P.valid & (1u << CI))) return 0u;
   const float ak = a[6 + (CI >> 1)];
   const float rx = P.cr[CI][0], ry = P.cr[CI][1], rz = P.cr[CI][2];
   const float px = a[0] + a[4] * rz - a[5] * ry + ak * P.cw[CI][0];
@@ -401,7 +405,8 @@ BRB_D unsigned contact_bits(const BrbModelConsts &c, const Phys &P, const float 
   const float z2 = mu * (P.cy[CI][2] - px);
   const unsigned pb = prev >> (4 * CI);
   const float e0 = (pb & 1u) ? eps : -eps, e1 = (pb & 2u) ? eps : -eps, e2 = (pb & 4u) ? eps : -eps, e3 = (pb & 8u) ? eps : -eps;
-  return ((unsigned)(z0 + z1 < e0) | ((unsigned)(z0 - z1 < e1) << 1) | ((unsigned)(z0 + z2 < e2) << 2) | ((unsigned)(z0 - z2 < e3) << 3)) << (4 * CI);
+  const unsigned nb = ((unsigned)(z0 + z1 < e0) | ((unsigned)(z0 - z1 < e1) << 1) | ((unsigned)(z0 + z2 < e2) << 2) | ((unsigned)(z0 - z2 < e3) << 3)) << (4 * CI);
+  return (P.valid & (1u << CI)) ? nb : 0u;
 }
 
 template <bool VI = false>
@@ -428,50 +433,42 @@ BRB_D void stab_fill(const BrbModelConsts &c, bool vi, int idx) {
 
 // ---- H += P_c' S P_c, r -= P_c' S yhat-ish for one contact; S = Pi' W_c Pi in world axes:
 //      Sxx = W22, Syy = W11, Szz = W00, Syz = W01, Sxz = -W02, Sxy = 0
-template <int CI, bool VI>
-BRB_D void contact_assemble(const BrbModelConsts &c, const Phys &P, unsigned bits, float (&H)[36], float (&r)[8]) {
-  const unsigned b = (bits >> (4 * CI)) & 15u;
-#ifdef BRB_TRIPSTATS
-  if (P.valid & (1u << CI)) atomicAdd(&g_trip[176 + b], 1ull);   // pyramid-row pattern of every contact at every solve
-#endif
-  if ((P.valid & (1u << CI)) && b) {
-    constexpr int kw = 6 + (CI >> 1);
-    // S for this row pattern from the 16-entry table in shared memory (stab_fill): 5 LDS on the otherwise idle LSU pipe
-    // instead of ~25 bit-to-float conversions and multiplies on the FP32 pipe
-    const float *t = g_stab + 5 * b;
-    float Szz = t[0], Syz = t[1], Sxz = t[2], Syy = t[3], Sxx = t[4];
-    if (VI) { const float Dc = P.cD[CI]; Szz *= Dc; Syz *= Dc; Sxz *= Dc; Syy *= Dc; Sxx *= Dc; }
-    const float rx = P.cr[CI][0], ry = P.cr[CI][1], rz = P.cr[CI][2];
-    const float wx = P.cw[CI][0], wy = P.cw[CI][1], wz = P.cw[CI][2];
-    // columns of P: e_x e_y e_z | cx=(0,-rz,ry) cy=(rz,0,-rx) cz=(-ry,rx,0) | w ;  T_j = S p_j
-    const float T3x = Sxz * ry, T3y = -Syy * rz + Syz * ry, T3z = -Syz * rz + Szz * ry;
-    const float T4x = Sxx * rz - Sxz * rx, T4y = -Syz * rx, T4z = Sxz * rz - Szz * rx;
-    const float T5x = -Sxx * ry, T5y = Syy * rx, T5z = -Sxz * ry + Syz * rx;
-    const float Twx = Sxx * wx + Sxz * wz, Twy = Syy * wy + Syz * wz, Twz = Sxz * wx + Syz * wy + Szz * wz;
-    H[LT(0, 0)] += Sxx; H[LT(2, 0)] += Sxz; H[LT(1, 1)] += Syy; H[LT(2, 1)] += Syz; H[LT(2, 2)] += Szz;
-    H[LT(3, 0)] += T3x; H[LT(3, 1)] += T3y; H[LT(3, 2)] += T3z;
-    H[LT(4, 0)] += T4x; H[LT(4, 1)] += T4y; H[LT(4, 2)] += T4z;
-    H[LT(5, 0)] += T5x; H[LT(5, 1)] += T5y; H[LT(5, 2)] += T5z;
-    H[LT(3, 3)] += -rz * T3y + ry * T3z;
-    H[LT(4, 3)] += rz * T3x - rx * T3z;
-    H[LT(5, 3)] += -ry * T3x + rx * T3y;
-    H[LT(4, 4)] += rz * T4x - rx * T4z;
-    H[LT(5, 4)] += -ry * T4x + rx * T4y;
-    H[LT(5, 5)] += -ry * T5x + rx * T5y;
-    H[LT(kw, 0)] += Twx; H[LT(kw, 1)] += Twy; H[LT(kw, 2)] += Twz;
-    H[LT(kw, 3)] += -rz * Twy + ry * Twz;
-    H[LT(kw, 4)] += rz * Twx - rx * Twz;
-    H[LT(kw, 5)] += -ry * Twx + rx * Twy;
-    H[LT(kw, kw)] += wx * Twx + wy * Twy + wz * Twz;
-    // rhs: g = -S yhat_w with yhat_w = (-y2, y1, y0) the contact-frame vector in world axes
-    const float y0 = P.cy[CI][0], y1 = P.cy[CI][1], y2 = P.cy[CI][2];
-    const float gx = Sxx * y2 - Sxz * y0, gy = -(Syy * y1 + Syz * y0), gz = Sxz * y2 - Syz * y1 - Szz * y0;
-    r[0] += gx; r[1] += gy; r[2] += gz;
-    r[3] += -rz * gy + ry * gz;
-    r[4] += rz * gx - rx * gz;
-    r[5] += -ry * gx + rx * gy;
-    r[kw] += wx * gx + wy * gy + wz * gz;
-  }
+// S5 = {Szz, Syz, Sxz, Syy, Sxx} of this slot's row pattern (all zero for a slot that is not in contact or has no active row).
+// Branch-free like contact_setup: the four slots interleave.
+template <int CI>
+BRB_D void contact_assemble(const Phys &P, const float (&S5)[5], float (&H)[36], float (&r)[8]) {
+  constexpr int kw = 6 + (CI >> 1);
+  const float Szz = S5[0], Syz = S5[1], Sxz = S5[2], Syy = S5[3], Sxx = S5[4];
+  const float rx = P.cr[CI][0], ry = P.cr[CI][1], rz = P.cr[CI][2];
+  const float wx = P.cw[CI][0], wy = P.cw[CI][1], wz = P.cw[CI][2];
+  // columns of P: e_x e_y e_z | cx=(0,-rz,ry) cy=(rz,0,-rx) cz=(-ry,rx,0) | w ;  T_j = S p_j
+  const float T3x = Sxz * ry, T3y = -Syy * rz + Syz * ry, T3z = -Syz * rz + Szz * ry;
+  const float T4x = Sxx * rz - Sxz * rx, T4y = -Syz * rx, T4z = Sxz * rz - Szz * rx;
+  const float T5x = -Sxx * ry, T5y = Syy * rx, T5z = -Sxz * ry + Syz * rx;
+  const float Twx = Sxx * wx + Sxz * wz, Twy = Syy * wy + Syz * wz, Twz = Sxz * wx + Syz * wy + Szz * wz;
+  H[LT(0, 0)] += Sxx; H[LT(2, 0)] += Sxz; H[LT(1, 1)] += Syy; H[LT(2, 1)] += Syz; H[LT(2, 2)] += Szz;
+  H[LT(3, 0)] += T3x; H[LT(3, 1)] += T3y; H[LT(3, 2)] += T3z;
+  H[LT(4, 0)] += T4x; H[LT(4, 1)] += T4y; H[LT(4, 2)] += T4z;
+  H[LT(5, 0)] += T5x; H[LT(5, 1)] += T5y; H[LT(5, 2)] += T5z;
+  H[LT(3, 3)] += -rz * T3y + ry * T3z;
+  H[LT(4, 3)] += rz * T3x - rx * T3z;
+  H[LT(5, 3)] += -ry * T3x + rx * T3y;
+  H[LT(4, 4)] += rz * T4x - rx * T4z;
+  H[LT(5, 4)] += -ry * T4x + rx * T4y;
+  H[LT(5, 5)] += -ry * T5x + rx * T5y;
+  H[LT(kw, 0)] += Twx; H[LT(kw, 1)] += Twy; H[LT(kw, 2)] += Twz;
+  H[LT(kw, 3)] += -rz * Twy + ry * Twz;
+  H[LT(kw, 4)] += rz * Twx - rx * Twz;
+  H[LT(kw, 5)] += -ry * Twx + rx * Twy;
+  H[LT(kw, kw)] += wx * Twx + wy * Twy + wz * Twz;
+  // rhs: g = -S yhat_w with yhat_w = (-y2, y1, y0) the contact-frame vector in world axes
+  const float y0 = P.cy[CI][0], y1 = P.cy[CI][1], y2 = P.cy[CI][2];
+  const float gx = Sxx * y2 - Sxz * y0, gy = -(Syy * y1 + Syz * y0), gz = Sxz * y2 - Syz * y1 - Szz * y0;
+  r[0] += gx; r[1] += gy; r[2] += gz;
+  r[3] += -rz * gy + ry * gz;
+  r[4] += rz * gx - rx * gz;
+  r[5] += -ry * gx + rx * gy;
+  r[kw] += wx * gx + wy * gy + wz * gz;
 }
 
 // ---- H = M' + sum P'SP (packed lower 8x8), r = f - sum P'S yhat for the active set `bits`
@@ -507,10 +504,24 @@ BRB_D void phys_assemble(const BrbModelConsts &c, const Phys &P, unsigned bits, 
     if ((bits & want) == want) atomicAdd(&g_trip[193], 1ull);
   }
 #endif
-  contact_assemble<0, VI>(c, P, bits, H, r);
-  contact_assemble<1, VI>(c, P, bits, H, r);
-  contact_assemble<2, VI>(c, P, bits, H, r);
-  contact_assemble<3, VI>(c, P, bits, H, r);
+  // row-pattern weights of all four slots up front from the 16-entry table in shared memory (stab_fill; pattern 0 = all-zero
+  // weights, also forced for a slot that is not in contact): the LDS latency overlaps with M' above
+  const unsigned vm = ((P.valid & 1u) ? 0xFu : 0u) | ((P.valid & 2u) ? 0xF0u : 0u) | ((P.valid & 4u) ? 0xF00u : 0u) | ((P.valid & 8u) ? 0xF000u : 0u);
+  const unsigned bm = bits & vm;
+  float S5[4][5];
+#pragma unroll
+  for (int ci = 0; ci < 4; ci++) {
+    const float *t = g_stab + 5 * ((bm >> (4 * ci)) & 15u);
+#ifdef BRB_TRIPSTATS
+    if (P.valid & (1u << ci)) atomicAdd(&g_trip[176 + ((bm >> (4 * ci)) & 15u)], 1ull);   // pyramid-row pattern of every contact at every solve
+#endif
+#pragma unroll
+    for (int k = 0; k < 5; k++) S5[ci][k] = VI ? t[k] * P.cD[ci] : t[k];
+  }
+  contact_assemble<0>(P, S5[0], H, r);
+  contact_assemble<1>(P, S5[1], H, r);
+  contact_assemble<2>(P, S5[2], H, r);
+  contact_assemble<3>(P, S5[3], H, r);
 }
 
 // ---- one Newton step on the active set `bits`: (M' + sum P'SP) a = f - sum P'S yhat   (A.8; exact for a fixed set)
@@ -761,6 +772,13 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
     st.bits = S.aset[i];
     st.valid_prev = 0xFu;     // keep the persisted active set as it is on the first substep of the step
     st.n_contact = st.n_solve = st.n_nonconv = st.n_slots = 0;
+    // contact records are read branch-free (with zero weights when the slot is not in contact): they must hold finite values
+#pragma unroll
+    for (int ci = 0; ci < 4; ci++) {
+      st.cD[ci] = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; k++) st.cr[ci][k] = st.cw[ci][k] = st.cy[ci][k] = 0.f;
+    }
   }
   const int nsub = c.frame_skip;
   KF qprev[4];
@@ -941,7 +959,18 @@ __global__ void BRB_STEP_BOUNDS(KIND) brb_step_kernel(const __grid_constant__ Br
       if ((long long)base >= S.n) break;
       tid = (long long)base + (threadIdx.x & 31u);
     }
+#ifdef BRB_TIMELINE
+    unsigned long long tl0; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl0));
+#endif
     step_batch<KIND>(c, S, perm, tid, ctasync && !queue, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u);
+#ifdef BRB_TIMELINE
+    if ((threadIdx.x & 31u) == 0u) {   // debug: one record per warp task {sm, warp slot, first robot of the visit order, start ns, end ns}
+      unsigned long long tl1; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(tl1));
+      unsigned smid, wid; asm volatile("mov.u32 %0, %%smid;" : "=r"(smid)); asm volatile("mov.u32 %0, %%warpid;" : "=r"(wid));
+      const unsigned long long slot = atomicAdd(&g_timeline[0], 1ull);
+      if (slot < (1ull << 16)) { unsigned long long *r = g_timeline + 1 + 4 * slot; r[0] = ((unsigned long long)smid << 32) | wid; r[1] = (unsigned long long)tid; r[2] = tl0; r[3] = tl1; }
+    }
+#endif
     if (!queue) break;
   }
 }
@@ -1130,6 +1159,13 @@ extern "C" void brb_launch_step(int kind, const BrbModelConsts *c, const BrbStat
   }
 }
 
+#ifdef BRB_TIMELINE
+extern "C" void brb_timeline(unsigned long long *out, int reset) {
+  cudaDeviceSynchronize();
+  if (out) cudaMemcpyFromSymbol(out, g_timeline, sizeof(g_timeline));
+  if (reset) { unsigned long long z = 0; cudaMemcpyToSymbol(g_timeline, &z, sizeof(z)); }
+}
+#endif
 #ifdef BRB_TRIPSTATS
 extern "C" void brb_tripstats(unsigned long long *out) { cudaMemcpyFromSymbol(out, g_trip, sizeof(unsigned long long) * (48 + 128 + 18)); }
 #endif
