@@ -216,6 +216,7 @@ BRB_D void reset_env(const BrbState &S, long long i, const double u[16], float o
 
 #ifdef BRB_TIMELINE
 __device__ unsigned long long g_timeline[1 + 4 * 65536];   // debug: per warp-task records of the step kernel
+__device__ unsigned g_tl_trips[65536 * 2];                 // debug: loop trips of the warp task that starts at visit-order position 32 k; sum of its lanes' solves
 #endif
 #ifdef BRB_TRIPSTATS
 __device__ unsigned long long g_trip[48 + 32 * 4 + 16 + 2];  // debug: warp-trips, lane-trips, warp-trips with a solve, lanes solving; [8+k]: trips with k lanes in contact; [48+4*key+cls]: robots by incoming group key and contact class of the step
@@ -241,6 +242,9 @@ struct Phys {
   unsigned valid, valid_prev;               // bit ci: contact slot ci (2*wheel + rim end) is in contact (valid_prev: at step entry)
   bool clampL, clampR;                      // servo sits on its forcerange (A.9)
   unsigned n_contact, n_solve, n_nonconv, n_slots;
+#ifdef BRB_TIMELINE
+  unsigned n_trips;
+#endif
 };
 
 BRB_D void phys_world_force(const BrbModelConsts &c, const Phys &P, float (&r)[8]) {
@@ -591,8 +595,14 @@ BRB_D void phys_run(const BrbModelConsts &c, Phys &P, int nsub, KF (&qstale)[4],
   // after the other (ncu source page: phys_finalize executed 1.5x per trip at 20 lanes).
   bool need_setup = true, done = false;
   unsigned was = P.valid_prev;
+#ifdef BRB_TIMELINE
+  P.n_trips = 0;
+#endif
   for (;;) {
     if (!__any_sync(wmask, !done)) break;
+#ifdef BRB_TIMELINE
+    P.n_trips++;
+#endif
     if (!done && need_setup) {
       phys_setup(c, P);
       const unsigned fresh = P.valid & ~was;     // slots that were not in contact a substep ago start with all four rows active
@@ -784,6 +794,9 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
   KF qprev[4];
   phys_run<BRB_MAXIT>(c, st, nsub, qprev, wmask);
   stat[0] = nsub; stat[1] = st.n_contact; stat[2] = st.n_solve; stat[3] = st.n_nonconv; stat[7] = st.n_slots;
+#ifdef BRB_TIMELINE
+  stat[8] = st.n_trips;
+#endif
   {
     // group key for the next step's visit order (no effect on results): robots are bucketed by which wheel-rim contact
     // slots they ended the step with, airborne ones by whether / when they will reach the floor during the next step
@@ -912,6 +925,12 @@ __device__ __forceinline__ void step_batch(const BrbModelConsts &c, const BrbSta
     const unsigned same = __match_any_sync(0xFFFFFFFFu, key);
     if (live && (threadIdx.x & 31u) == (unsigned)(__ffs(same) - 1)) atomicAdd(&perm.hist[key], (unsigned)__popc(same));
   }
+#ifdef BRB_TIMELINE
+  {
+    const unsigned long long ns = warp_sum(stat[2]), nc = warp_sum(stat[1]);
+    if ((threadIdx.x & 31) == 0 && tid < 65536 * 32) { g_tl_trips[2 * (tid >> 5)] = stat[8]; g_tl_trips[2 * (tid >> 5) + 1] = (unsigned)(ns - nc); }
+  }
+#endif
   // statistics: one atomic per warp per counter
   const unsigned long long a0 = warp_sum(stat[0]), a1 = warp_sum(stat[1]), a2 = warp_sum(stat[2]), a3 = warp_sum(stat[3]),
                            a4 = warp_sum(stat[4]), a5 = warp_sum(stat[5]), a6 = warp_sum(live ? 1u : 0u), a7 = warp_sum(stat[7]),
@@ -1162,7 +1181,7 @@ extern "C" void brb_launch_step(int kind, const BrbModelConsts *c, const BrbStat
 #ifdef BRB_TIMELINE
 extern "C" void brb_timeline(unsigned long long *out, int reset) {
   cudaDeviceSynchronize();
-  if (out) cudaMemcpyFromSymbol(out, g_timeline, sizeof(g_timeline));
+  if (out) { cudaMemcpyFromSymbol(out, g_timeline, sizeof(g_timeline)); cudaMemcpyFromSymbol(out + 1 + 4 * 65536, g_tl_trips, sizeof(g_tl_trips)); }
   if (reset) { unsigned long long z = 0; cudaMemcpyToSymbol(g_timeline, &z, sizeof(z)); }
 }
 #endif

@@ -9,7 +9,7 @@ env = make_vec("Env01-v2", n, seed=0); env.reset()
 gen = torch.Generator(device="cuda").manual_seed(1234)
 acts = [torch.rand((n, 2), device="cuda", generator=gen) * 2 - 1 for _ in range(8)]
 L = _cabi.lib()
-buf = np.zeros(1 + 4 * 65536, np.uint64)
+buf = np.zeros(1 + 4 * 65536 + 65536, np.uint64)
 for k in range(100): env.step(acts[k % 8])
 L.brb_timeline(None, 1)
 env.step(acts[0])
@@ -35,4 +35,12 @@ ts = np.linspace(0, t1.max(), 23)[1:-1]
 print("resident warp-tasks over time:", [(round(float(t)), int(((t0 <= t) & (t1 > t)).sum())) for t in ts])
 second = t0 > 5.0
 print(f"tasks started after 5 us: {second.sum()}, their mean duration {dur[second].mean() if second.any() else 0:.1f} us, mean start {t0[second].mean() if second.any() else 0:.1f}")
+tr = buf[1 + 4 * 65536:].view(np.uint32).reshape(-1, 2)
+trips = tr[first // 32, 0].astype(int); extra = tr[first // 32, 1].astype(int)
+ex = dur > 0.8 * np.percentile(dur, 60)
+print("expensive tasks:", ex.sum(), "trips percentiles 10/50/90/99/100:", [int(np.percentile(trips[ex], p)) for p in (10, 50, 90, 99, 100)],
+      "us per trip:", round(float((dur[ex] / trips[ex]).mean()), 3), "+-", round(float((dur[ex] / trips[ex]).std()), 3))
+print("corr(duration, trips) among expensive:", round(float(np.corrcoef(dur[ex], trips[ex])[0, 1]), 3), " extra solves summed over lanes, mean:", extra[ex].mean())
+top = np.argsort(-dur)[:10]
+print("10 longest tasks: dur", dur[top].round(0), "trips", trips[top], "sm", sm[top])
 np.save("gpurun_out/r2_timeline.npy", r)
