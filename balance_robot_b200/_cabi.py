@@ -29,7 +29,7 @@ STAT_NAMES = ("substeps", "contact_substeps", "solves", "nonconverged", "unsuppo
 
 EXPORTS = (
     "brb_version", "brb_strerror", "brb_model_create", "brb_model_destroy", "brb_env_create", "brb_env_destroy",
-    "brb_env_reset_all", "brb_env_step", "brb_env_step_host", "brb_env_step_host_compact", "brb_env_get_state", "brb_env_set_state",
+    "brb_env_reset_all", "brb_env_step", "brb_env_step_host", "brb_env_step_host_compact", "brb_env_host_layout", "brb_env_get_state", "brb_env_set_state",
     "brb_env_get_elapsed", "brb_env_get_stats", "brb_env_num_envs", "brb_env_num_launches", "brb_fp32_peak_flops", "brb_policy_act", "brb_ppo_grad", "brb_adam_clip_step", "brb_policy_value_masked", "brb_ppo_tc_fault",
     "brb_comm_create", "brb_comm_export", "brb_comm_open", "brb_comm_destroy", "brb_comm_grad", "brb_comm_fault", "brb_comm_allreduce_adam",
 )
@@ -83,6 +83,7 @@ def lib() -> C.CDLL:
     L.brb_env_step.argtypes = [vp] * 11
     L.brb_env_step_host.argtypes = [vp] * 9
     L.brb_env_step_host_compact.argtypes = [vp] * 7 + [i64]
+    L.brb_env_host_layout.argtypes = [vp, C.POINTER(i64 * 3), C.POINTER(i64)]
     L.brb_env_get_state.argtypes = [vp] * 5
     L.brb_env_set_state.argtypes = [vp] * 4
     L.brb_env_get_elapsed.argtypes = [vp] * 3

@@ -21,7 +21,7 @@ void brb_launch_group(long long n, const uint8_t *key, const unsigned *hist, uns
 void brb_launch_reset(int kind, const BrbState *S, float *obs, const double *replay_u, unsigned epoch, cudaStream_t stream);
 void brb_launch_done_rows(long long n, const uint8_t *done, const uint8_t *truncated, const float *terminal_obs, const float *ep_return,
                           const int32_t *ep_len, unsigned *block_count, unsigned *block_base, unsigned *ticket, int *n_done,
-                          uint32_t *rows, cudaStream_t stream);
+                          uint32_t *rows, long long max_rows, cudaStream_t stream);
 void brb_launch_get_state(const BrbState *S, double *qpos, double *qvel, double *xquat, cudaStream_t stream);
 void brb_launch_set_state(const BrbState *S, const double *qpos, const double *qvel, cudaStream_t stream);
 void brb_launch_get_elapsed(const BrbState *S, int32_t *out, cudaStream_t stream);
@@ -52,7 +52,8 @@ struct BrbEnv {
   // finished-episode compaction for brb_env_step_host_compact
   unsigned *d_blk_count, *d_blk_base, *d_ticket;   // [ceil(N/256)] x 2, [1] ticket followed by [1] n_done
   uint32_t *d_rows;                                // [N][BRB_DONE_ROW_WORDS]
-  int32_t *h_ndone;                                // pinned
+  int32_t *h_ndone;                                // pinned (mapped: the count kernel writes it directly)
+  int32_t *h_ndone_dev;                            // device-side address of h_ndone
   cudaStream_t host_stream;
   // reset_all / set_state run on the caller's stream, the host-buffer step on host_stream: the next host step waits for this event
   cudaEvent_t user_ev;
@@ -125,7 +126,7 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
       align_up(NQ * N * 8), align_up(NV * N * 8), align_up(4 * N * 8), align_up(8 * N * 4), align_up(N * 8), align_up(N * 8),
       align_up(3 * N * 8), align_up(N * 4), align_up(N * 4), align_up(N * 4), align_up(BRB_NSTATS * 8), align_up(N * 4), align_up(N), align_up(4 * 32 * 4 + 64),
       // staging
-      align_up(2 * N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(N), align_up(N), align_up(N * 4),
+      align_up(2 * N * 4), align_up(6 * N * 4), align_up(N * 4), align_up(N), align_up(6 * N * 4), align_up(N * 4), align_up(N), align_up(N * 4),
       // finished-episode compaction
       align_up(((N + 255) / 256) * 4), align_up(((N + 255) / 256) * 4), align_up(2 * 4), align_up(N * BRB_DONE_ROW_WORDS * 4)};
   size_t total = 0;
@@ -150,11 +151,11 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
   e->keys = TAKE(uint8_t);
   e->hist = TAKE(unsigned);
   e->d_actions = TAKE(float);
-  e->d_obs = TAKE(float);
+  e->d_obs = TAKE(float);       // obs | reward | done are adjacent: one device-to-host copy on the host path
   e->d_reward = TAKE(float);
+  e->d_done = TAKE(uint8_t);
   e->d_tobs = TAKE(float);
   e->d_epret = TAKE(float);
-  e->d_done = TAKE(uint8_t);
   e->d_trunc = TAKE(uint8_t);
   e->d_eplen = TAKE(int32_t);
   e->d_blk_count = TAKE(unsigned);
@@ -174,6 +175,7 @@ extern "C" int brb_env_create(const BrbModel *m, int64_t n, uint64_t seed, int64
   e->max_ctas = getenv("BRB_NO_QUEUE") ? 0 : brb_step_resident_ctas(m->consts.env_kind, m->device);
   if (cudaStreamCreateWithFlags(&e->host_stream, cudaStreamNonBlocking) != cudaSuccess) { cudaFree(e->arena); free(e); return BRB_ECUDA; }
   if (cudaMallocHost(&e->h_ndone, sizeof(int32_t)) != cudaSuccess) { cudaStreamDestroy(e->host_stream); cudaFree(e->arena); free(e); return BRB_ENOMEM; }
+  if (cudaHostGetDevicePointer((void **)&e->h_ndone_dev, e->h_ndone, 0) != cudaSuccess) { cudaGetLastError(); e->h_ndone_dev = nullptr; }
   if (cudaEventCreateWithFlags(&e->user_ev, cudaEventDisableTiming) != cudaSuccess) { cudaFreeHost(e->h_ndone); cudaStreamDestroy(e->host_stream); cudaFree(e->arena); free(e); return BRB_ECUDA; }
   *out = e;
   return BRB_OK;
@@ -261,28 +263,70 @@ extern "C" int brb_env_step_host(BrbEnv *e, const float *actions, float *obs, fl
   return BRB_OK;
 }
 
+// BRB_PROFILE_HOST=1 (kernel-tuning experiments): host-side time line of the host-buffer step, printed every 256 calls
+#include <chrono>
+static double hostprof_acc[4]; static long hostprof_n; static int hostprof_on = -1;
+#define HOSTPROF_T(k) std::chrono::steady_clock::time_point hp_t##k; if (hostprof_on < 0) hostprof_on = getenv("BRB_PROFILE_HOST") ? 1 : 0; if (hostprof_on) hp_t##k = std::chrono::steady_clock::now()
+#define HOSTPROF_END() do { if (hostprof_on) { hostprof_acc[0] += std::chrono::duration<double, std::micro>(hp_t1 - hp_t0).count(); \
+  hostprof_acc[1] += std::chrono::duration<double, std::micro>(hp_t2 - hp_t1).count(); hostprof_acc[2] += std::chrono::duration<double, std::micro>(hp_t3 - hp_t2).count(); \
+  if (++hostprof_n % 256 == 0) { fprintf(stderr, "[brb host path] H2D enqueue %.1f us, launches + D2H enqueue %.1f us, wait %.1f us\n", hostprof_acc[0] / 256, hostprof_acc[1] / 256, hostprof_acc[2] / 256); hostprof_acc[0] = hostprof_acc[1] = hostprof_acc[2] = 0; } } } while (0)
+
+// device-side address of a pinned (page-locked, mapped) host buffer, or NULL for pageable memory
+static void *mapped_device_ptr(const void *host) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, host) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return a.type == cudaMemoryTypeHost ? a.devicePointer : nullptr;
+}
+
+extern "C" int brb_env_host_layout(const BrbEnv *e, int64_t offsets[3], int64_t *total_bytes) {
+  if (!e || !offsets || !total_bytes) return BRB_EINVAL;
+  offsets[0] = 0;
+  offsets[1] = (char *)e->d_reward - (char *)e->d_obs;
+  offsets[2] = (char *)e->d_done - (char *)e->d_obs;
+  *total_bytes = offsets[2] + e->S.n;
+  return BRB_OK;
+}
+
 extern "C" int brb_env_step_host_compact(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, int32_t *n_done,
                                          uint32_t *done_rows, int64_t max_rows) {
   if (!e || !actions || !obs || !n_done || (max_rows > 0 && !done_rows) || max_rows < 0) return BRB_EINVAL;
   ON_DEVICE(e->model->device);
   const size_t N = (size_t)e->S.n;
   cudaStream_t s = e->host_stream;
+  HOSTPROF_T(0);
   if (e->user_ev_pending) { CK(cudaStreamWaitEvent(s, e->user_ev, 0)); e->user_ev_pending = 0; }
   CK(cudaMemcpyAsync(e->d_actions, actions, 2 * N * sizeof(float), cudaMemcpyHostToDevice, s));
+  HOSTPROF_T(1);
   launch_step(e, e->d_actions, e->d_obs, e->d_reward, e->d_done, e->d_trunc, e->d_tobs, e->d_epret, e->d_eplen, nullptr, s);
+  // finished-episode rows: when the caller's row buffer is pinned the compaction kernel writes the rows (and the count) straight
+  // into host memory over PCIe -- a few KB of posted writes -- so the call needs ONE stream synchronisation; a pageable buffer
+  // takes the count first and the rows in a second copy
+  uint32_t *rows_dev = (max_rows > 0 && e->h_ndone_dev) ? (uint32_t *)mapped_device_ptr(done_rows) : nullptr;
+  const bool direct = rows_dev != nullptr || (max_rows == 0 && e->h_ndone_dev);
   brb_launch_done_rows(e->S.n, e->d_done, e->d_trunc, e->d_tobs, e->d_epret, e->d_eplen, e->d_blk_count, e->d_blk_base, e->d_ticket,
-                       (int *)(e->d_ticket + 1), e->d_rows, s);
+                       direct ? (int *)e->h_ndone_dev : (int *)(e->d_ticket + 1), direct ? rows_dev : e->d_rows, direct ? (long long)max_rows : (long long)N, s);
   e->launches += 2;
   CK(cudaGetLastError());
-  CK(cudaMemcpyAsync(e->h_ndone, e->d_ticket + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
-  CK(cudaMemcpyAsync(obs, e->d_obs, 6 * N * sizeof(float), cudaMemcpyDeviceToHost, s));
-  if (reward) CK(cudaMemcpyAsync(reward, e->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, s));
-  if (done) CK(cudaMemcpyAsync(done, e->d_done, N, cudaMemcpyDeviceToHost, s));
+  if (!direct) CK(cudaMemcpyAsync(e->h_ndone, e->d_ticket + 1, sizeof(int32_t), cudaMemcpyDeviceToHost, s));
+  // obs | reward | done leave in one copy when the host buffers are laid out like the device staging block (brb_env_host_layout)
+  const ptrdiff_t off_r = (char *)e->d_reward - (char *)e->d_obs, off_d = (char *)e->d_done - (char *)e->d_obs;
+  // (having the step kernel write obs / reward into the pinned buffers itself was measured slower: 981 vs 907 us per step --
+  // scattered 24-byte PCIe writes bunch up when the expensive warps finish together)
+  if (reward && done && (char *)reward - (char *)obs == off_r && (char *)done - (char *)obs == off_d) {
+    CK(cudaMemcpyAsync(obs, e->d_obs, (size_t)off_d + N, cudaMemcpyDeviceToHost, s));
+  } else {
+    CK(cudaMemcpyAsync(obs, e->d_obs, 6 * N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (reward) CK(cudaMemcpyAsync(reward, e->d_reward, N * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (done) CK(cudaMemcpyAsync(done, e->d_done, N, cudaMemcpyDeviceToHost, s));
+  }
+  HOSTPROF_T(2);
   CK(cudaStreamSynchronize(s));
+  HOSTPROF_T(3);
+  HOSTPROF_END();
   const int32_t nd = *e->h_ndone;
   *n_done = nd;
   if (nd > max_rows) return BRB_EINVAL;
-  if (nd > 0) {
+  if (nd > 0 && !direct) {
     CK(cudaMemcpyAsync(done_rows, e->d_rows, (size_t)nd * BRB_DONE_ROW_WORDS * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
   }

@@ -938,7 +938,52 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
   if (truncated) truncated[i] = (uint8_t)(trunc && !terminated);
   if (ep_return_out) ep_return_out[i] = (float)epr;
   if (ep_len_out) ep_len_out[i] = epl;
-  stat[4] = es.unsupported ? 1u : 0u;
+  // poses whose contacts this kernel does not model, evaluated on the post-step state like Env01's count: chassis on the floor,
+  // a wheel lying flat, and a wheel within reach of the block (conservative separating-axis test on the block's face normals, the
+  // wheel axis and the centre line: "not separated on these five axes" over-counts, it never misses a touching pair)
+  {
+    const double w = qpos[3], x = qpos[4], y = qpos[5], z = qpos[6];
+    const double R[3][3] = {{1 - 2 * (y * y + z * z), 2 * (x * y - w * z), 2 * (x * z + w * y)}, {2 * (x * y + w * z), 1 - 2 * (x * x + z * z), 2 * (y * z - w * x)},
+                            {2 * (x * z - w * y), 2 * (y * z + w * x), 1 - 2 * (x * x + y * y)}};
+    const double n0 = R[2][0], n1 = R[2][1], n2 = R[2][2];
+    const double hz = qpos[2] - ((double)c.zfloor + (double)c.zfloor_lo);
+    const double low = hz + n2 * (double)c.chassis_pos[2] + n0 * (double)c.chassis_pos[0] + n1 * (double)c.chassis_pos[1]
+                       - fabs(n0) * (double)c.chassis_half[0] - fabs(n1) * (double)c.chassis_half[1] - fabs(n2) * (double)c.chassis_half[2];
+    const double rho = sqrt(n1 * n1 + n2 * n2);
+    const double tri = hz + (double)c.oz * n2 - fabs(n0) * ((double)c.ox + (double)c.hl) + 0.5 * (double)c.rad * rho;
+    bool near_wheel = false;
+    const double bw = qpos[12], bx = qpos[13], by = qpos[14], bz = qpos[15];
+    const double E[3][3] = {{1 - 2 * (by * by + bz * bz), 2 * (bx * by + bw * bz), 2 * (bx * bz - bw * by)},      // block axes as rows
+                            {2 * (bx * by - bw * bz), 1 - 2 * (bx * bx + bz * bz), 2 * (by * bz + bw * bx)},
+                            {2 * (bx * bz + bw * by), 2 * (by * bz - bw * bx), 1 - 2 * (bx * bx + by * by)}};
+    const double ax[3] = {R[0][0], R[1][0], R[2][0]};                                                       // wheel axes = chassis x
+    for (int k = 0; k < 2; k++) {
+      const double sg = k ? 1.0 : -1.0, ox = sg * (double)c.ox, oz = (double)c.oz;
+      const double d[3] = {qpos[9] - (qpos[0] + R[0][0] * ox + R[0][2] * oz), qpos[10] - (qpos[1] + R[1][0] * ox + R[1][2] * oz),
+                           qpos[11] - (qpos[2] + R[2][0] * ox + R[2][2] * oz)};
+      const double dl = sqrt(d[0] * d[0] + d[1] * d[1] + d[2] * d[2]);
+      bool sep = false;
+      for (int a = 0; a < 5 && !sep; a++) {
+        double L[3];
+        if (a < 3) { L[0] = E[a][0]; L[1] = E[a][1]; L[2] = E[a][2]; }
+        else if (a == 3) { L[0] = ax[0]; L[1] = ax[1]; L[2] = ax[2]; }
+        else { if (dl < 1e-9) break; L[0] = d[0] / dl; L[1] = d[1] / dl; L[2] = d[2] / dl; }
+        const double la = L[0] * ax[0] + L[1] * ax[1] + L[2] * ax[2];
+        const double sc = (double)c.hl * fabs(la) + (double)c.rad * sqrt(fmax(0.0, 1.0 - la * la));
+        double sb = 0.0;
+        for (int e = 0; e < 3; e++) sb += (double)c.blk_half * fabs(L[0] * E[e][0] + L[1] * E[e][1] + L[2] * E[e][2]);
+        sep = fabs(L[0] * d[0] + L[1] * d[1] + L[2] * d[2]) > sc + sb + (double)c.pp[2][7];
+      }
+      near_wheel = near_wheel || !sep;
+    }
+#ifdef BRB_PROBE_UNSUP   // kernel-tuning experiment: count one cause at a time (1 = chassis-floor, 2 = wheel flat, 4 = wheel near block)
+    stat[4] = (((BRB_PROBE_UNSUP & 1) && low <= 0.0) || ((BRB_PROBE_UNSUP & 2) && tri <= 0.0) || ((BRB_PROBE_UNSUP & 4) && near_wheel)) ? 1u : 0u;
+#else
+    stat[4] = (low <= 0.0 || tri <= 0.0 || near_wheel) ? 1u : 0u;
+#endif
+    if (low <= 0.0) es.unsupported |= 1u;
+    if (near_wheel) es.unsupported |= 2u;
+  }
   if (dn) {
     stat[5] = 1;
     stat[6] = 0;

@@ -1051,12 +1051,13 @@ __global__ void brb_done_count_kernel(long long n, const uint8_t *__restrict__ d
   }
   unsigned base = part[threadIdx.x] - sum;
   for (unsigned b = lo; b < hi; b++) { block_base[b] = base; base += ((volatile unsigned *)block_count)[b]; }
-  if (threadIdx.x == blockDim.x - 1) { *n_done = (int)part[threadIdx.x]; *ticket = 0u; }
+  if (threadIdx.x == blockDim.x - 1) { *n_done = (int)part[threadIdx.x]; *ticket = 0u; }     // n_done may be mapped host memory
 }
 
 __global__ void brb_done_rows_kernel(long long n, const uint8_t *__restrict__ done, const uint8_t *__restrict__ truncated,
                                      const float *__restrict__ terminal_obs, const float *__restrict__ ep_return,
-                                     const int32_t *__restrict__ ep_len, const unsigned *__restrict__ block_base, uint32_t *__restrict__ rows) {
+                                     const int32_t *__restrict__ ep_len, const unsigned *__restrict__ block_base, uint32_t *__restrict__ rows,
+                                     long long max_rows) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const bool d = i < n && done[i] != 0;
   __shared__ unsigned wcount[8];
@@ -1067,6 +1068,7 @@ __global__ void brb_done_rows_kernel(long long n, const uint8_t *__restrict__ do
   if (!d) return;
   unsigned r = block_base[blockIdx.x] + __popc(bal & ((1u << lane) - 1u));
   for (unsigned k = 0; k < w; k++) r += wcount[k];
+  if ((long long)r >= max_rows) return;     // rows may be the caller's (mapped, pinned) host buffer: never write past its capacity
   uint32_t *row = rows + (size_t)r * BRB_DONE_ROW_WORDS;
   row[0] = (uint32_t)i;
 #pragma unroll
@@ -1196,10 +1198,10 @@ extern "C" void brb_launch_group(long long n, const uint8_t *key, const unsigned
 
 extern "C" void brb_launch_done_rows(long long n, const uint8_t *done, const uint8_t *truncated, const float *terminal_obs, const float *ep_return,
                                      const int32_t *ep_len, unsigned *block_count, unsigned *block_base, unsigned *ticket, int *n_done,
-                                     uint32_t *rows, cudaStream_t stream) {
+                                     uint32_t *rows, long long max_rows, cudaStream_t stream) {
   const unsigned nb = (unsigned)((n + 255) / 256);
   brb_done_count_kernel<<<nb, 256, 0, stream>>>(n, done, block_count, block_base, ticket, n_done);
-  brb_done_rows_kernel<<<nb, 256, 0, stream>>>(n, done, truncated, terminal_obs, ep_return, ep_len, block_base, rows);
+  brb_done_rows_kernel<<<nb, 256, 0, stream>>>(n, done, truncated, terminal_obs, ep_return, ep_len, block_base, rows, max_rows);
 }
 
 // epoch = number of earlier reset_all calls on this env object: VecEnv.reset() called again draws NEW start states (block index

@@ -179,9 +179,16 @@ class BalanceVecEnv:
         if output == "numpy":
             pin = dict(pin_memory=True)
             self._h_act = torch.zeros((n, 2), dtype=torch.float32, **pin)
-            self._hbuf = [dict(obs=torch.zeros((n, 6), dtype=torch.float32, **pin), rew=torch.zeros(n, dtype=torch.float32, **pin),
-                               done=torch.zeros(n, dtype=torch.uint8, **pin),
-                               rows=torch.zeros((n, _cabi.DONE_ROW_WORDS), dtype=torch.float32, **pin)) for _ in range(2)]
+            # obs | reward | done of a buffer set live in ONE pinned block laid out like the device staging block, so that they
+            # come back in a single device-to-host copy; the finished-episode rows are written into `rows` by the device directly
+            offs, total = (C.c_int64 * 3)(), C.c_int64()
+            _cabi.check(L.brb_env_host_layout(self._env, C.byref(offs), C.byref(total)), "brb_env_host_layout")
+            self._hbuf = []
+            for _ in range(2):
+                blk = torch.zeros(total.value, dtype=torch.uint8, **pin)
+                self._hbuf.append(dict(block=blk, obs=blk[offs[0]:offs[0] + 24 * n].view(torch.float32).view(n, 6),
+                                       rew=blk[offs[1]:offs[1] + 4 * n].view(torch.float32), done=blk[offs[2]:offs[2] + n],
+                                       rows=torch.zeros((n, _cabi.DONE_ROW_WORDS), dtype=torch.float32, **pin)))
             self._h_ndone = torch.zeros(1, dtype=torch.int32, **pin)
             self._flip = 0
         self._actions = None

@@ -112,6 +112,12 @@ int brb_env_step_host(BrbEnv *e, const float *actions, float *obs, float *reward
 int brb_env_step_host_compact(BrbEnv *e, const float *actions, float *obs, float *reward, uint8_t *done, int32_t *n_done,
                               uint32_t *done_rows, int64_t max_rows);
 
+/* Byte offsets of obs / reward / done inside the device staging block of the host path (offsets[0] = 0) and its total size.
+ * A caller that carves its three host buffers out of ONE pinned allocation at these offsets gets them back in a single
+ * device-to-host copy from brb_env_step_host_compact; any other layout is served by three copies.  (A pinned done_rows
+ * buffer is written by the compaction kernel directly, a pageable one through a second copy.) */
+int brb_env_host_layout(const BrbEnv *e, int64_t offsets[3], int64_t *total_bytes);
+
 /* MujocoEnv.set_state / data.qpos, data.qvel access (trajectory checks).  xquat = the (stale, Q1) chassis
  * quaternion the observation functions read; may be NULL. */
 int brb_env_get_state(BrbEnv *e, double *qpos, double *qvel, double *xquat, void *stream);
