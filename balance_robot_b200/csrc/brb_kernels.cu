@@ -533,8 +533,8 @@ template <bool VI = false>
 BRB_D void phys_solve(const BrbModelConsts &c, Phys &P, unsigned bits, float (&a)[8]) {
   float H[36], r[8];
   phys_assemble<VI>(c, P, bits, H, r);
-  // Cholesky H = L L' and the two triangular solves, straight-line (generated: gen_chol8.py)
-#include "brb_chol8.inc"
+  // Cholesky H = L L' and the two triangular solves, straight-line (generated: gen_chol8.py; H(1,0) is structurally zero here)
+#include "brb_chol8z.inc"
 #pragma unroll
   for (int k = 0; k < 8; k++) a[k] = r[k];
   P.n_solve++;
@@ -583,13 +583,83 @@ BRB_D void phys_finalize(const BrbModelConsts &c, Phys &P, float avx, float avy,
 // lane; a lane whose active set changed simply repeats the solve in the next trip while its neighbours move on to
 // their next substep, so a warp pays max-over-lanes(nsub + extra solves) trips instead of nsub * max-over-lanes
 // (solves per substep).  qstale receives the quaternion before the last integration (Q1).
+// One loop trip.  (A second copy of this body without the `done` tests for the first nsub trips -- no lane can be finished before --
+// was measured slower: 0.893 vs 0.776 ms, the two copies no longer fit the instruction cache together.)
+template <int MAXIT>
+BRB_D void phys_trip(const BrbModelConsts &c, Phys &P, const int nsub, KF (&qstale)[4], const unsigned wmask, int &sidx, int &it,
+                     bool &need_setup, bool &done, unsigned &was) {
+  const bool live = !done;
+  if (live && need_setup) {
+    phys_setup(c, P);
+    const unsigned fresh = P.valid & ~was;     // slots that were not in contact a substep ago start with all four rows active
+    P.bits |= ((fresh & 1u) ? 0xFu : 0u) | ((fresh & 2u) ? 0xF0u : 0u) | ((fresh & 4u) ? 0xF00u : 0u) | ((fresh & 8u) ? 0xF000u : 0u);
+    was = P.valid;
+    need_setup = false;
+    it = 0;
+  }
+  bool conv = true;
+  float avx, avy, avz, ab0, ab1, ab2, a6, a7;
+#ifdef BRB_TRIPSTATS
+  {
+    const unsigned act = __ballot_sync(wmask, live);
+    const unsigned nv = __popc(__ballot_sync(wmask, live && P.valid != 0u));
+    if ((threadIdx.x & 31u) == (unsigned)(__ffs(wmask) - 1)) {
+      atomicAdd(&g_trip[0], 1ull); atomicAdd(&g_trip[1], (unsigned long long)__popc(act));
+      if (nv) { atomicAdd(&g_trip[2], 1ull); atomicAdd(&g_trip[3], (unsigned long long)nv); }
+      atomicAdd(&g_trip[8 + nv], 1ull);
+    }
+  }
+#endif
+  __syncwarp(wmask);
+  if (live) {
+    if (P.valid) {
+      float a[8];
+      phys_solve(c, P, P.bits, a);
+      const unsigned nb = phys_active_set(c, P, a, P.bits);
+      conv = (nb == P.bits);
+      P.bits = nb;
+      if (!conv && ++it >= MAXIT) { P.n_nonconv++; conv = true; }
+      avx = a[0]; avy = a[1]; avz = a[2];
+      ab0 = P.ex[0] * a[3] + P.ex[1] * a[4] + P.ex[2] * a[5];      // alpha_b = R' alpha_w
+      ab1 = P.ey[0] * a[3] + P.ey[1] * a[4] + P.ey[2] * a[5];
+      ab2 = P.ez[0] * a[3] + P.ez[1] * a[4] + P.ez[2] * a[5];
+      a6 = a[6]; a7 = a[7];
+    } else {
+      // free flight: a_b = M_b^-1 f_b in the chassis frame, linear part rotated to the world
+      const float mg = c.mass * c.grav;
+      const float f[8] = {P.fb[0] - mg * P.ex[2], P.fb[1] - mg * P.ey[2], P.fb[2] - mg * P.ez[2], P.fb[3], P.fb[4], P.fb[5], P.fb[6], P.fb[7]};
+      const float u0 = c.minv_xy[0] * f[0] + c.minv_xy[1] * f[4];
+      const float u1 = c.minv_blk[0] * f[1] + c.minv_blk[1] * f[3] + c.minv_blk[2] * f[6] + c.minv_blk[3] * f[7];
+      const float u2 = c.minv_uz * f[2];
+      avx = P.ex[0] * u0 + P.ey[0] * u1 + P.ez[0] * u2;
+      avy = P.ex[1] * u0 + P.ey[1] * u1 + P.ez[1] * u2;
+      avz = P.ex[2] * u0 + P.ey[2] * u1 + P.ez[2] * u2;
+      ab0 = c.minv_blk[1] * f[1] + c.minv_blk[4] * f[3] + c.minv_blk[5] * f[6] + c.minv_blk[6] * f[7];
+      ab1 = c.minv_xy[1] * f[0] + c.minv_xy[2] * f[4];
+      ab2 = c.minv_wz * f[5];
+      a6 = c.minv_blk[2] * f[1] + c.minv_blk[5] * f[3] + c.minv_blk[7] * f[6] + c.minv_blk[8] * f[7];
+      a7 = c.minv_blk[3] * f[1] + c.minv_blk[6] * f[3] + c.minv_blk[8] * f[6] + c.minv_blk[9] * f[7];
+    }
+  }
+  __syncwarp(wmask);
+  if (live && conv) {
+    if (sidx == nsub - 1) {
+#pragma unroll
+      for (int k = 0; k < 4; k++) qstale[k] = P.q[k];
+    }
+    phys_finalize(c, P, avx, avy, avz, ab0, ab1, ab2, a6, a7);
+    if (++sidx >= nsub) done = true;
+    need_setup = true;
+  }
+}
+
 template <int MAXIT>
 BRB_D void phys_run(const BrbModelConsts &c, Phys &P, int nsub, KF (&qstale)[4], const unsigned wmask) {
   int sidx = 0, it = 0;
   // The active set of a new substep is seeded with the previous substep's converged set (rows of a contact that just
-  // appeared start "all active"): right ~97 % of the time, and the post-solve check below catches the rest.
-  // phys_setup has a single call site (flag instead of a second inlined copy) to keep the loop body small.
-  // The loop is warp-uniform: lanes that finished keep circulating (idle) until every lane of `wmask` (the lanes of this
+  // appeared start "all active"): right ~97 % of the time, and the post-solve check catches the rest.
+  // phys_setup has a single call site per loop (flag instead of a second inlined copy) to keep the loop body small.
+  // The loops are warp-uniform: lanes that finished keep circulating (idle) until every lane of `wmask` (the lanes of this
   // warp that run a robot) is done, which makes the __syncwarp()s legal.  They are there because the compiler otherwise
   // threads the free-flight branch straight into the integration code and the two halves of a mixed warp run it one
   // after the other (ncu source page: phys_finalize executed 1.5x per trip at 20 lanes).
@@ -603,68 +673,7 @@ BRB_D void phys_run(const BrbModelConsts &c, Phys &P, int nsub, KF (&qstale)[4],
 #ifdef BRB_TIMELINE
     P.n_trips++;
 #endif
-    if (!done && need_setup) {
-      phys_setup(c, P);
-      const unsigned fresh = P.valid & ~was;     // slots that were not in contact a substep ago start with all four rows active
-      P.bits |= ((fresh & 1u) ? 0xFu : 0u) | ((fresh & 2u) ? 0xF0u : 0u) | ((fresh & 4u) ? 0xF00u : 0u) | ((fresh & 8u) ? 0xF000u : 0u);
-      was = P.valid;
-      need_setup = false;
-      it = 0;
-    }
-    bool conv = true;
-    float avx, avy, avz, ab0, ab1, ab2, a6, a7;
-#ifdef BRB_TRIPSTATS
-    {
-      const unsigned act = __ballot_sync(wmask, !done);
-      const unsigned nv = __popc(__ballot_sync(wmask, !done && P.valid != 0u));
-      if ((threadIdx.x & 31u) == (unsigned)(__ffs(wmask) - 1)) {
-        atomicAdd(&g_trip[0], 1ull); atomicAdd(&g_trip[1], (unsigned long long)__popc(act));
-        if (nv) { atomicAdd(&g_trip[2], 1ull); atomicAdd(&g_trip[3], (unsigned long long)nv); }
-        atomicAdd(&g_trip[8 + nv], 1ull);
-      }
-    }
-#endif
-    __syncwarp(wmask);
-    if (!done) {
-      if (P.valid) {
-        float a[8];
-        phys_solve(c, P, P.bits, a);
-        const unsigned nb = phys_active_set(c, P, a, P.bits);
-        conv = (nb == P.bits);
-        P.bits = nb;
-        if (!conv && ++it >= MAXIT) { P.n_nonconv++; conv = true; }
-        avx = a[0]; avy = a[1]; avz = a[2];
-        ab0 = P.ex[0] * a[3] + P.ex[1] * a[4] + P.ex[2] * a[5];      // alpha_b = R' alpha_w
-        ab1 = P.ey[0] * a[3] + P.ey[1] * a[4] + P.ey[2] * a[5];
-        ab2 = P.ez[0] * a[3] + P.ez[1] * a[4] + P.ez[2] * a[5];
-        a6 = a[6]; a7 = a[7];
-      } else {
-        // free flight: a_b = M_b^-1 f_b in the chassis frame, linear part rotated to the world
-        const float mg = c.mass * c.grav;
-        const float f[8] = {P.fb[0] - mg * P.ex[2], P.fb[1] - mg * P.ey[2], P.fb[2] - mg * P.ez[2], P.fb[3], P.fb[4], P.fb[5], P.fb[6], P.fb[7]};
-        const float u0 = c.minv_xy[0] * f[0] + c.minv_xy[1] * f[4];
-        const float u1 = c.minv_blk[0] * f[1] + c.minv_blk[1] * f[3] + c.minv_blk[2] * f[6] + c.minv_blk[3] * f[7];
-        const float u2 = c.minv_uz * f[2];
-        avx = P.ex[0] * u0 + P.ey[0] * u1 + P.ez[0] * u2;
-        avy = P.ex[1] * u0 + P.ey[1] * u1 + P.ez[1] * u2;
-        avz = P.ex[2] * u0 + P.ey[2] * u1 + P.ez[2] * u2;
-        ab0 = c.minv_blk[1] * f[1] + c.minv_blk[4] * f[3] + c.minv_blk[5] * f[6] + c.minv_blk[6] * f[7];
-        ab1 = c.minv_xy[1] * f[0] + c.minv_xy[2] * f[4];
-        ab2 = c.minv_wz * f[5];
-        a6 = c.minv_blk[2] * f[1] + c.minv_blk[5] * f[3] + c.minv_blk[7] * f[6] + c.minv_blk[8] * f[7];
-        a7 = c.minv_blk[3] * f[1] + c.minv_blk[6] * f[3] + c.minv_blk[8] * f[6] + c.minv_blk[9] * f[7];
-      }
-    }
-    __syncwarp(wmask);
-    if (!done && conv) {
-      if (sidx == nsub - 1) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) qstale[k] = P.q[k];
-      }
-      phys_finalize(c, P, avx, avy, avz, ab0, ab1, ab2, a6, a7);
-      if (++sidx >= nsub) done = true;
-      need_setup = true;
-    }
+    phys_trip<MAXIT>(c, P, nsub, qstale, wmask, sidx, it, need_setup, done, was);
   }
 }
 
