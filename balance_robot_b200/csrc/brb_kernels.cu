@@ -299,6 +299,8 @@ BRB_D RimDist rim_dist_fp64(const BrbModelConsts &c, const KF (&q)[4], const KF 
 // scheduler interleaves; with one divergent region per slot the kernel ran 13 % slower although it executed fewer
 // instructions (a warp is latency-bound here: profiles/README.md, round 2).  A slot that is not in contact gets finite
 // values that nothing reads: its row pattern is forced to 0 (all-zero weights) in phys_assemble / phys_active_set.
+// (Skipping a wheel's two slots behind a warp-uniform vote when no lane has that wheel on the floor was also slower, 0.826 vs
+// 0.760 ms: on this path any branch costs more than the work it saves.)
 template <int CI, bool VI>
 BRB_D void contact_setup(const BrbModelConsts &c, Phys &P, float dist, float sa, const float (&G)[3], const float (&A)[3],
                          const float (&B2)[3], const float (&ww)[3]) {
