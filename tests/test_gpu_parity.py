@@ -259,6 +259,50 @@ def test_host_step_compact_equals_full_host_step():
     a.close(); b.close()
 
 
+def test_host_step_compact_with_pageable_buffers_and_any_layout():
+    """The compact host call must not depend on HOW the caller allocated its buffers: pinned block laid out as
+    brb_env_host_layout says (one copy, rows written by the device), or separate pageable numpy arrays (three copies, rows
+    in a second copy) -- same bytes out.  Also the capacity error: more finished envs than max_rows -> BRB_EINVAL."""
+    import ctypes as C
+    from balance_robot_b200 import _cabi
+    n = 5000                                   # not a multiple of 64: the staging offsets carry alignment padding
+    a = make_vec("Env01-v2", n, seed=9, output="numpy")
+    b = make_vec("Env01-v2", n, seed=9, output="numpy")
+    a.reset(); b.reset()
+    L = _cabi.lib()
+    offs, total = (C.c_int64 * 3)(), C.c_int64()
+    _cabi.check(L.brb_env_host_layout(a._env, C.byref(offs), C.byref(total)), "brb_env_host_layout")
+    assert offs[0] == 0 and offs[1] >= 24 * n and offs[2] >= offs[1] + 4 * n and total.value == offs[2] + n
+    obs = np.zeros((n, 6), np.float32); rew = np.zeros(n, np.float32); done = np.zeros(n, np.uint8)
+    rows = np.zeros((n, _cabi.DONE_ROW_WORDS), np.float32); nd = np.zeros(1, np.int32)
+    rng = np.random.default_rng(2)
+    seen = 0
+    for k in range(40):
+        act = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        _cabi.check(L.brb_env_step_host_compact(a._env, act.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data,
+                                                nd.ctypes.data, rows.ctypes.data, n), "brb_env_step_host_compact")
+        o2, r2, d2, infos = b.step(act)
+        assert np.array_equal(obs, o2) and np.array_equal(rew, r2) and np.array_equal(done.astype(bool), d2)
+        assert int(nd[0]) == len(infos._idx) == int(done.sum())
+        assert np.array_equal(rows[:int(nd[0])].view(np.int32)[:, 0], infos._idx)
+        if nd[0]:
+            i = int(infos._idx[0])
+            assert np.array_equal(infos[i]["terminal_observation"], rows[0, 1:7])
+        seen += int(nd[0])
+    assert seen > 100
+    # capacity error (pageable and pinned row buffers alike): run until some env finishes with room for no row at all
+    for k in range(200):
+        act = rng.uniform(-1, 1, (n, 2)).astype(np.float32)
+        rc = L.brb_env_step_host_compact(a._env, act.ctypes.data, obs.ctypes.data, rew.ctypes.data, done.ctypes.data, nd.ctypes.data, None, 0)
+        if nd[0] > 0:
+            assert rc == -22, rc          # BRB_EINVAL
+            break
+        assert rc == 0
+    else:
+        raise AssertionError("no episode finished")
+    a.close(); b.close()
+
+
 def test_full_size_properties():
     """BASELINE.json configs[1] size (65,536 envs): determinism, unit quaternions, finite state, episode accounting."""
     n = 65536
