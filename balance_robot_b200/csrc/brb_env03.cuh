@@ -932,12 +932,6 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
   obs_of(p_true, pitch_dot, qvel[6], qvel[7], 0.0, 0.0, o);
   const double epr = S.ep_return[i] + rew;
   const int epl = S.ep_len[i] + 1;
-  const bool dn = terminated || trunc;
-  if (reward) reward[i] = (float)rew;
-  if (done) done[i] = (uint8_t)dn;
-  if (truncated) truncated[i] = (uint8_t)(trunc && !terminated);
-  if (ep_return_out) ep_return_out[i] = (float)epr;
-  if (ep_len_out) ep_len_out[i] = epl;
   // poses whose contacts this kernel does not model, evaluated on the post-step state like Env01's count: chassis on the floor,
   // a wheel lying flat, and a wheel within reach of the block (conservative separating-axis test on the block's face normals, the
   // wheel axis and the centre line: "not separated on these five axes" over-counts, it never misses a touching pair)
@@ -984,6 +978,13 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
     if (low <= 0.0) es.unsupported |= 1u;
     if (near_wheel) es.unsupported |= 2u;
   }
+  const bool cut = stat[4] != 0u && (c.flags & BRB_FLAG_TRUNCATE_UNSUPPORTED) != 0;      // opt-in: end the episode as truncated
+  const bool dn = terminated || trunc || cut;
+  if (reward) reward[i] = (float)rew;
+  if (done) done[i] = (uint8_t)dn;
+  if (truncated) truncated[i] = (uint8_t)((trunc || cut) && !terminated);
+  if (ep_return_out) ep_return_out[i] = (float)epr;
+  if (ep_len_out) ep_len_out[i] = epl;
   if (dn) {
     stat[5] = 1;
     stat[6] = 0;

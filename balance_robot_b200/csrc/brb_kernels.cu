@@ -844,13 +844,6 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
   obs_of(pitch, pitch_dot, qvel[6], qvel[7], tws, 0.0, o);
   const double epr = S.ep_return[i] + rew;
   const int epl = S.ep_len[i] + 1;
-  const bool dn = terminated || trunc;
-  if (reward) reward[i] = (float)rew;
-  if (done) done[i] = (uint8_t)dn;
-  if (truncated) truncated[i] = (uint8_t)(trunc && !terminated);
-  if (ep_return_out) ep_return_out[i] = (float)epr;
-  if (ep_len_out) ep_len_out[i] = epl;
-
   // poses whose contacts this kernel does not model (chassis-floor, wheel lying flat): count them
   {
     const double w = xq[0], x = xq[1], y = xq[2], z = xq[3];
@@ -862,6 +855,14 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
     const double tri = hz + (double)c.oz * n2 - fabs(n0) * ((double)c.ox + (double)c.hl) + 0.5 * (double)c.rad * rho;
     stat[4] = (low <= 0.0 || tri <= 0.0) ? 1u : 0u;
   }
+  const bool cut = stat[4] != 0u && (c.flags & BRB_FLAG_TRUNCATE_UNSUPPORTED) != 0;      // opt-in: end the episode as truncated
+
+  const bool dn = terminated || trunc || cut;
+  if (reward) reward[i] = (float)rew;
+  if (done) done[i] = (uint8_t)dn;
+  if (truncated) truncated[i] = (uint8_t)((trunc || cut) && !terminated);
+  if (ep_return_out) ep_return_out[i] = (float)epr;
+  if (ep_len_out) ep_len_out[i] = epl;
 
   if (dn) {
     stat[5] = 1;

@@ -82,7 +82,7 @@ def _skew(v):
 
 
 def compile_model(spec: ModelSpec, env_kind: int, max_episode_steps: int, frame_skip: int = 250,
-                  actderiv_skip_clamped: bool = True) -> RobotModel:
+                  actderiv_skip_clamped: bool = True, truncate_unsupported: bool = False) -> RobotModel:
     # ---- class checks ------------------------------------------------------------------------
     free_roots = [b for b in range(1, len(spec.bodies)) if spec.bodies[b].joint >= 0
                   and spec.joints[spec.bodies[b].joint].type == JNT_FREE]
@@ -290,7 +290,7 @@ def compile_model(spec: ModelSpec, env_kind: int, max_episode_steps: int, frame_
         hb = bgeoms[0].size[0]
         c.blk_half, c.blk_mass, c.blk_inertia, c.blk_radius = hb, bb.mass, Ib[0, 0], hb * math.sqrt(3.0)
         c.chassis_radius = float(np.linalg.norm(chassis_geoms[0].size))
-    c.flags = 1 if actderiv_skip_clamped else 0
+    c.flags = (1 if actderiv_skip_clamped else 0) | (2 if truncate_unsupported else 0)     # include/brb.h BRB_FLAG_*
 
     # MuJoCo accumulates data.time += h once per substep in fp64; reproduce the exact sequence
     # (np.cumsum adds sequentially, left to right, exactly like the C loop `time += h`)

@@ -31,6 +31,10 @@ extern "C" {
 #define BRB_ENV03_V2 3 /* reference balance_robot/__init__.py:47-52 -> envs/env03_v2.py:14 (robot + fired block) */
 
 #define BRB_FLAG_ACTDERIV_SKIP_CLAMPED 1
+/* Opt-in (off by default: the reference has no such rule): an env whose step ends in a pose with contacts the kernels do not
+ * generate (BRB_STAT_UNSUPPORTED) is ended as TRUNCATED (TimeLimit.truncated = True, so a trainer bootstraps the value) and
+ * auto-reset, instead of stepping on with those contacts missing. */
+#define BRB_FLAG_TRUNCATE_UNSUPPORTED 2
 
 #define BRB_NSTATS 12
 #define BRB_STAT_SUBSTEPS 0          /* env-substeps executed */

@@ -78,3 +78,24 @@ def test_full_size_properties_and_block_cycle():
     assert st["episodes"] == tot_done and st["env_steps"] == 160 * n
     assert st["nonconverged"] < 1e-4 * st["substeps"]
     env.close()
+
+
+def test_truncate_unsupported_flag_ends_the_episode_instead_of_stepping_on():
+    """BRB_FLAG_TRUNCATE_UNSUPPORTED (opt-in): a robot whose wheel comes within reach of the block -- a pair the kernels generate
+    no contact for -- is ended as truncated and reset; with the flag off (default, the reference's semantics) it is only counted."""
+    n, steps = 16384, 150
+    on = make_vec("Env03-v2", n, seed=1, truncate_unsupported=True)
+    off = make_vec("Env03-v2", n, seed=1)
+    on.reset(); off.reset()
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    cuts = 0
+    for _ in range(steps):
+        act = torch.rand((n, 2), device="cuda", generator=gen) * 2 - 1
+        _, _, d, info = on.step(act)
+        cuts += int((info.truncated.bool() & (info.episode_length < 1200)).sum())
+        _, _, _, info_off = off.step(act)
+        assert int(info_off.truncated.sum()) == 0                      # 150 steps: no TimeLimit truncation, and no cut without the flag
+    u_on, u_off = on.stats()["unsupported"], off.stats()["unsupported"]
+    assert u_off > 0 and u_on > 0
+    assert 0.5 * u_on <= cuts <= u_on, (cuts, u_on)                     # a flagged step that also terminated (pitch) is not "truncated"
+    on.close(); off.close()
