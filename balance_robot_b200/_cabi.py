@@ -30,7 +30,7 @@ STAT_NAMES = ("substeps", "contact_substeps", "solves", "nonconverged", "unsuppo
 EXPORTS = (
     "brb_version", "brb_strerror", "brb_model_create", "brb_model_destroy", "brb_env_create", "brb_env_destroy",
     "brb_env_reset_all", "brb_env_step", "brb_env_step_host", "brb_env_step_host_compact", "brb_env_host_layout", "brb_env_get_state", "brb_env_set_state",
-    "brb_env_get_elapsed", "brb_env_get_stats", "brb_env_num_envs", "brb_env_num_launches", "brb_fp32_peak_flops", "brb_policy_act", "brb_ppo_grad", "brb_adam_clip_step", "brb_policy_value_masked", "brb_ppo_tc_fault",
+    "brb_env_get_elapsed", "brb_env_get_stats", "brb_env_num_envs", "brb_env_num_launches", "brb_fp32_peak_flops", "brb_policy_act", "brb_ppo_grad", "brb_adam_clip_step", "brb_random_permutation", "brb_policy_value_masked", "brb_ppo_tc_fault",
     "brb_comm_create", "brb_comm_export", "brb_comm_open", "brb_comm_destroy", "brb_comm_grad", "brb_comm_fault", "brb_comm_allreduce_adam",
 )
 
@@ -107,6 +107,7 @@ def lib() -> C.CDLL:
     L.brb_comm_allreduce_adam.argtypes = [vp, vp, vp, vp] + [C.c_float] * 4 + [i64, C.c_float, vp, vp]
     L.brb_policy_value_masked.argtypes = [vp, vp, vp, i64, vp, vp]
     L.brb_adam_clip_step.argtypes = [vp] * 4 + [i64] + [C.c_float] * 4 + [i64, C.c_float, C.c_float, vp, vp]
+    L.brb_random_permutation.argtypes = [vp, i64, u64, vp]
     _lib = L
     return L
 

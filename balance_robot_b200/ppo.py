@@ -377,8 +377,15 @@ class PPO:
         b1, b2 = self.optimizer.param_groups[0]["betas"]
         self._gflat.zero_(); self._gstats.zero_()
         updates = 0
+        if getattr(self, "_perm", None) is None or self._perm.numel() != total:
+            self._perm = torch.empty(total, dtype=torch.int64, device=self.device)
+        perm = self._perm
         for _ in range(cfg.n_epochs):
-            perm = torch.randperm(total, device=self.device, generator=self.gen)
+            # minibatch order of this epoch: keyed bijection of [0, total) written by one kernel (csrc/brb_policy.cu), no sort
+            self._perm_calls = getattr(self, "_perm_calls", 0) + 1
+            with torch.cuda.device(self.device):
+                _cabi.check(L.brb_random_permutation(perm.data_ptr(), total, (int(cfg.seed) * 1000003 + self._perm_calls) & (2 ** 64 - 1), stream),
+                            "brb_random_permutation")
             for k in range(cfg.n_minibatches):
                 idx = perm[k * mb:(k + 1) * mb]
                 if cfg.normalize_advantage and mb > 1:

@@ -169,6 +169,10 @@ int brb_ppo_grad(const float *params, const float *obs, const float *actions, co
                  const int64_t *idx, int64_t mb, const float *adv_stats, float clip_range, float vf_coef, float ent_coef, float *grad,
                  float *stats, void *stream);
 
+/* out[0..n) <- a pseudo-random permutation of 0..n-1 keyed by `seed` (device pointer, int64): the minibatch order of one epoch of
+ * SB3 PPO.train() (RolloutBuffer.get -> np.random.permutation; third party, reference src/sb_rl.py:63-71) without a sort. */
+int brb_random_permutation(int64_t *out, int64_t n, uint64_t seed, void *stream);
+
 /* One optimiser step on the flat parameter block, fused into one launch: g = grad * grad_scale (1 / world after an all-reduce
  * sum), th.nn.utils.clip_grad_norm_(max_grad_norm) (<= 0: no clipping), torch.optim.Adam (SB3 PPO.train(): policy.optimizer.step(),
  * third party; reference src/sb_rl.py:63-71).  m / v = Adam moments [n], step = 1-based step count, norm_out (nullable) receives

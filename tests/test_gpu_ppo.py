@@ -196,3 +196,25 @@ def test_ppo_learns_to_balance_env01_v3_with_sb3_style_settings():
     assert first["ep_len_mean"] < 100, first
     assert best > 1500, (first, best)
     env.close()
+
+
+def test_random_permutation_kernel_is_a_keyed_bijection():
+    """brb_random_permutation: every value of [0, n) exactly once for sizes on and off powers of two, different keys give different
+    orders, and the order looks shuffled (a minibatch of consecutive output positions covers the index range evenly)."""
+    import ctypes as C
+    from balance_robot_b200 import _cabi
+    L = _cabi.lib()
+    for n in (1, 2, 3, 1000, 4096, 65536 * 16 + 17, 1 << 24):
+        out = torch.empty(n, dtype=torch.int64, device="cuda")
+        _cabi.check(L.brb_random_permutation(out.data_ptr(), n, 12345, None), "brb_random_permutation")
+        torch.cuda.synchronize()
+        assert torch.equal(torch.sort(out).values, torch.arange(n, device="cuda")), n
+        if n >= 1000:
+            out2 = torch.empty_like(out)
+            _cabi.check(L.brb_random_permutation(out2.data_ptr(), n, 12346, None), "brb_random_permutation")
+            assert (out != out2).float().mean() > 0.99
+            assert (out == torch.arange(n, device="cuda")).float().mean() < 0.01               # few fixed points
+            q = out[: n // 4].double()
+            assert abs(q.mean().item() / (n - 1) - 0.5) < 0.05 and abs(q.std().item() / (n - 1) - 12 ** -0.5) < 0.03     # uniform over the range
+            d = (out[1:] - out[:-1]).double()
+            assert abs(torch.corrcoef(torch.stack([out[:-1].double(), out[1:].double()]))[0, 1].item()) < 0.05, n       # neighbours unrelated
