@@ -439,12 +439,237 @@ int env03_coupled_solve(const BrbModelConsts &c, const Phys &P, const GContact *
   return nonconv;
 }
 
+// ------------------------------------------------------------------------------------------------ wheel-block (cylinder-box)
+// MuJoCo 3.2.0 sends this pair to libccd's MPR (mjc_Convex), an iterative portal refinement whose result on the curved wheel surface
+// is only good to its tolerance; it is not restated.  Own analytic collider, the oracle's algorithm (oracle/brb_ref.c:
+// brb_ref_cylinder_box) in fp32: sep(d) = d.(c_box - c_cyl) - h_cyl(d) - h_box(d) is a lower bound of the signed distance for every
+// unit d and the distance is its maximum; it is evaluated on the directions at which the maximum can sit -- box face normals, the
+// wheel axis, axis x box edge, the radial direction to each box vertex, from the nearest rim point of either cap to each vertex, and
+// the best direction perpendicular to each box edge direction (one-dimensional scan + golden-section search, fixed step count).  One contact: normal from the wheel to
+// the block, position from two alternating projections between the two support features.  Rare path: not inlined, loops not unrolled.
+#define CYLBOX_TAU 0.02f
+BRB_D float soft_signf(float x) { return fmaxf(-1.f, fminf(1.f, x / CYLBOX_TAU)); }
+BRB_D float cyl_box_sep(const float *d, const float *delta, const float *a, float R, float L, const float (*E)[3], float h) {
+  const float da = dot3f(d, a);
+  return dot3f(d, delta) - L * fabsf(da) - R * sqrtf(fmaxf(0.f, 1.f - da * da)) - h * (fabsf(dot3f(d, E[0])) + fabsf(dot3f(d, E[1])) + fabsf(dot3f(d, E[2])));
+}
+BRB_D void cyl_box_try(const float *v, bool orient, const float *delta, const float *a, float R, float L, const float (*E)[3], float h, float &best, float *bd) {
+  const float n2 = dot3f(v, v);
+  if (n2 <= 1e-16f) return;
+  float in = 1.f / sqrtf(n2);
+  if (orient && dot3f(v, delta) < 0.f) in = -in;
+  const float t[3] = {v[0] * in, v[1] * in, v[2] * in};
+  const float sp = cyl_box_sep(t, delta, a, R, L, E, h);
+  if (sp > best) { best = sp; bd[0] = t[0]; bd[1] = t[1]; bd[2] = t[2]; }
+}
+BRB_D float cyl_box_cos16(int k) {      // cos(2 pi k / 16); sin = entry (k + 12) & 15
+  const int q = k & 7;                  // cos(pi - x) = -cos(x): fold to the first half, then to the first quadrant
+  const float v = q == 0 ? 1.f : (q == 1 ? 0.92387953251128674f : (q == 2 ? 0.70710678118654752f : (q == 3 ? 0.38268343236508977f :
+                  (q == 4 ? 0.f : (q == 5 ? -0.38268343236508977f : (q == 6 ? -0.70710678118654752f : -0.92387953251128674f))))));
+  return (k & 8) ? -v : v;
+}
+BRB_D float cyl_box_g(float c, float s, float D1, float D2, float A1, float A2, float R, float L, float h) {
+  const float da = A1 * c + A2 * s;
+  return D1 * c + D2 * s - L * fabsf(da) - R * sqrtf(fmaxf(0.f, 1.f - da * da)) - h * (fabsf(c) + fabsf(s));
+}
+#ifdef BRB_HOST_EMU
+static
+#else
+__device__ __noinline__
+#endif
+int env03_cyl_box(const float *cc, const float *a, float R, float L, const float *b, const float (*E)[3], float h, float margin,
+                  float *dist_out, float *nrm, float *pos) {
+  const float delta[3] = {b[0] - cc[0], b[1] - cc[1], b[2] - cc[2]};
+  float best = -1e30f, bd[3] = {0.f, 0.f, 1.f};
+#pragma unroll 1
+  for (int i = 0; i < 3; i++) cyl_box_try(E[i], true, delta, a, R, L, E, h, best, bd);
+  cyl_box_try(a, true, delta, a, R, L, E, h, best, bd);
+#pragma unroll 1
+  for (int i = 0; i < 3; i++) {
+    const float x[3] = {a[1] * E[i][2] - a[2] * E[i][1], a[2] * E[i][0] - a[0] * E[i][2], a[0] * E[i][1] - a[1] * E[i][0]};
+    if (dot3f(x, x) > 1e-10f) cyl_box_try(x, true, delta, a, R, L, E, h, best, bd);
+  }
+#pragma unroll 1
+  for (int vi = 0; vi < 8; vi++) {
+    float u[3];
+    for (int k = 0; k < 3; k++) u[k] = delta[k] + ((vi & 1) ? h : -h) * E[0][k] + ((vi & 2) ? h : -h) * E[1][k] + ((vi & 4) ? h : -h) * E[2][k];
+    const float ua = dot3f(u, a), up[3] = {u[0] - ua * a[0], u[1] - ua * a[1], u[2] - ua * a[2]};
+    const float rho2 = dot3f(up, up);
+    if (rho2 <= 1e-16f) continue;
+    cyl_box_try(up, false, delta, a, R, L, E, h, best, bd);
+#pragma unroll 1
+    for (int cap = 0; cap < 2; cap++) {
+      const float sg = cap ? -1.f : 1.f, ir = R / sqrtf(rho2);
+      float t[3];
+      for (int k = 0; k < 3; k++) t[k] = u[k] - sg * L * a[k] - up[k] * ir;
+      cyl_box_try(t, false, delta, a, R, L, E, h, best, bd);
+    }
+  }
+  // box edge against a rim / the curved side / a cap: the separating direction is perpendicular to the edge, d(phi) = cos(phi) E_a1 +
+  // sin(phi) E_a2; sep restricted to that plane is a one-dimensional function (all four parallel edges and both caps at once), maximised
+  // by a 16-point scan and a golden-section search with a fixed number of steps inside the best cell (no trigonometry per step)
+#pragma unroll 1
+  for (int ax = 0; ax < 3; ax++) {
+    const int a1 = (ax + 1) % 3, a2 = (ax + 2) % 3;
+    const float D1 = dot3f(E[a1], delta), D2 = dot3f(E[a2], delta), A1 = dot3f(E[a1], a), A2 = dot3f(E[a2], a);
+    int kb = 0;
+    float gb = -1e30f;
+#pragma unroll 1
+    for (int k = 0; k < 16; k++) {
+      const float g = cyl_box_g(cyl_box_cos16(k), cyl_box_cos16((k + 12) & 15), D1, D2, A1, A2, R, L, h);
+      if (g > gb) { gb = g; kb = k; }
+    }
+    const float ck = cyl_box_cos16(kb), sk = cyl_box_cos16((kb + 12) & 15), tmax = 0.41421356237309503f, gr = 0.6180339887498949f;
+    float lo = -tmax, hi = tmax, x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo), f1 = 0.f, f2 = 0.f;
+    int fresh = 2;
+#pragma unroll 1
+    for (int it = 0; it < 14; it++) {
+#pragma unroll 1
+      for (int w = 0; w < 2; w++) {
+        if (fresh != 2 && w != fresh) continue;
+        const float t = w ? x2 : x1, in = 1.f / sqrtf(1.f + t * t);
+        const float g = cyl_box_g((ck - t * sk) * in, (sk + t * ck) * in, D1, D2, A1, A2, R, L, h);
+        if (w) f2 = g; else f1 = g;
+      }
+      if (f1 > f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); fresh = 0; }
+      else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); fresh = 1; }
+    }
+    const float t = 0.5f * (lo + hi), in = 1.f / sqrtf(1.f + t * t), cf = (ck - t * sk) * in, sf = (sk + t * ck) * in;
+    float td[3];
+    for (int k = 0; k < 3; k++) td[k] = cf * E[a1][k] + sf * E[a2][k];
+    cyl_box_try(td, false, delta, a, R, L, E, h, best, bd);
+  }
+  if (best > margin) return 0;
+  // contact point: support features along bd refined by two alternating projections; feature selection blended over 0.02 rad around
+  // perpendicular (see the oracle: continuous from the middle of a flat-on-flat patch to its deeper end)
+  const float sa = soft_signf(dot3f(bd, a));
+  float sb[3], rdir[3] = {0.f, 0.f, 0.f}, wr = 0.f;
+  for (int j = 0; j < 3; j++) sb[j] = soft_signf(dot3f(bd, E[j]));
+  {
+    const float da = dot3f(bd, a), dp[3] = {bd[0] - da * a[0], bd[1] - da * a[1], bd[2] - da * a[2]}, pm = sqrtf(dot3f(dp, dp));
+    if (pm > 1e-12f) { for (int k = 0; k < 3; k++) rdir[k] = dp[k] / pm; wr = fminf(1.f, pm / CYLBOX_TAU); }
+  }
+  float pc[3], qb[3];
+  for (int k = 0; k < 3; k++) pc[k] = cc[k] + sa * L * a[k] + wr * R * rdir[k];
+#pragma unroll 1
+  for (int pass = 0; pass < 2; pass++) {
+    for (int k = 0; k < 3; k++) qb[k] = b[k];
+    const float rel[3] = {pc[0] - b[0], pc[1] - b[1], pc[2] - b[2]};
+    for (int j = 0; j < 3; j++) {
+      const float l = -sb[j] * h + (1.f - fabsf(sb[j])) * fmaxf(-h, fminf(h, dot3f(rel, E[j])));
+      for (int k = 0; k < 3; k++) qb[k] += l * E[j][k];
+    }
+    const float rl[3] = {qb[0] - cc[0], qb[1] - cc[1], qb[2] - cc[2]}, ta = dot3f(rl, a);
+    const float t = sa * L + (1.f - fabsf(sa)) * fmaxf(-L, fminf(L, ta));
+    float rv[3];
+    for (int k = 0; k < 3; k++) rv[k] = rl[k] - ta * a[k];
+    { const float n2 = dot3f(rv, rv); if (n2 > R * R) { const float in = R / sqrtf(n2); for (int k = 0; k < 3; k++) rv[k] *= in; } }
+    for (int k = 0; k < 3; k++) pc[k] = cc[k] + t * a[k] + wr * R * rdir[k] + (1.f - wr) * rv[k];
+  }
+  *dist_out = best;
+  for (int k = 0; k < 3; k++) { nrm[k] = bd[k]; pos[k] = 0.5f * (pc[k] + qb[k]); }
+  return 1;
+}
+
+// Wheel-block contacts of the current substep: at most one per wheel, each with its own frame and the wheel's column of the point map
+// (the contact point rides on the spinning wheel).  Run-time indexed -> local memory; only touched while a wheel is within reach of the block.
+struct WBSet {
+  float n[2][3], t1[2][3], t2[2][3];
+  float ra[2][3], rb[2][3], w[2][3], y[2][3], D[2];
+  int wheel[2];
+  int nw;
+  unsigned bits;      // 4 pyramid rows per contact
+  bool near;          // the narrow phase ran for a wheel this substep
+};
+
+BRB_D void wb_setup(const BrbModelConsts &c, const Phys &P, const Blk &B, WBSet &W) {
+  W.nw = 0;
+  W.near = false;
+  if (!(c.flags & BRB_FLAG_WHEEL_BLOCK)) return;
+  const float *pp = c.pp[2];
+  const float reach = c.blk_radius + sqrtf(c.rad * c.rad + c.hl * c.hl) + pp[7];
+#pragma unroll 1
+  for (int k = 0; k < 2; k++) {
+    const float sg = k ? 1.f : -1.f;
+    float cw[3];
+    for (int j = 0; j < 3; j++) cw[j] = P.p[j].s + P.ex[j] * (sg * c.ox) + P.ez[j] * c.oz;
+    const float dx = B.p[0] - cw[0], dy = B.p[1] - cw[1], dz = B.p[2] - cw[2];
+    if (dx * dx + dy * dy + dz * dz > reach * reach) continue;
+    const float ax[3] = {P.ex[0], P.ex[1], P.ex[2]};
+    const float Bx[3][3] = {{B.ex[0], B.ex[1], B.ex[2]}, {B.ey[0], B.ey[1], B.ey[2]}, {B.ez[0], B.ez[1], B.ez[2]}};
+    {
+      // mid phase: separated by more than the margin along a box face normal or the wheel axis?  (four of the collider's own candidate
+      // directions: if one of them already exceeds the margin so does the maximum, i.e. the collider would return "no contact")
+      const float dl[3] = {dx, dy, dz};
+      bool sepd = false;
+#pragma unroll
+      for (int q = 0; q < 4; q++) {
+        const float *Lq = q < 3 ? Bx[q] : ax;
+        const float la = dot3f(Lq, ax);
+        const float sc = c.hl * fabsf(la) + c.rad * sqrtf(fmaxf(0.f, 1.f - la * la));
+        const float sbx = c.blk_half * (fabsf(dot3f(Lq, Bx[0])) + fabsf(dot3f(Lq, Bx[1])) + fabsf(dot3f(Lq, Bx[2])));
+        sepd = sepd || (fabsf(dot3f(Lq, dl)) - sc - sbx > pp[7]);
+      }
+      if (sepd) continue;
+    }
+    W.near = true;
+    float dist, nn[3], pos[3];
+    if (!env03_cyl_box(cw, ax, c.rad, c.hl, B.p, Bx, c.blk_half, pp[7], &dist, nn, pos)) continue;
+    if (dist >= pp[7]) continue;
+    const int m = W.nw++;
+    float t1[3], t2[3];
+    make_frame3(nn, t1, t2);
+    const float wr[3] = {P.ex[0] * P.w[0].s + P.ey[0] * P.w[1].s + P.ez[0] * P.w[2].s, P.ex[1] * P.w[0].s + P.ey[1] * P.w[1].s + P.ez[1] * P.w[2].s,
+                         P.ex[2] * P.w[0].s + P.ey[2] * P.w[1].s + P.ez[2] * P.w[2].s};
+    const float wb[3] = {B.ex[0] * B.w[0] + B.ey[0] * B.w[1] + B.ez[0] * B.w[2], B.ex[1] * B.w[0] + B.ey[1] * B.w[1] + B.ez[1] * B.w[2],
+                         B.ex[2] * B.w[0] + B.ey[2] * B.w[1] + B.ez[2] * B.w[2]};
+    float ra[3], rb[3], rc[3];
+    for (int j = 0; j < 3; j++) { ra[j] = pos[j] - P.p[j].s; rb[j] = pos[j] - B.p[j]; rc[j] = pos[j] - cw[j]; }
+    // wheel column: velocity of the material point per unit wheel speed = axis_k x (r - wheel centre), axis_k = sg ex
+    const float wv[3] = {sg * (ax[1] * rc[2] - ax[2] * rc[1]), sg * (ax[2] * rc[0] - ax[0] * rc[2]), sg * (ax[0] * rc[1] - ax[1] * rc[0])};
+    const float sk = P.s[k].s;
+    const float dv[3] = {(B.v[0] + wb[1] * rb[2] - wb[2] * rb[1]) - (P.v[0].s + wr[1] * ra[2] - wr[2] * ra[1] + sk * wv[0]),
+                         (B.v[1] + wb[2] * rb[0] - wb[0] * rb[2]) - (P.v[1].s + wr[2] * ra[0] - wr[0] * ra[2] + sk * wv[1]),
+                         (B.v[2] + wb[0] * rb[1] - wb[1] * rb[0]) - (P.v[2].s + wr[0] * ra[1] - wr[1] * ra[0] + sk * wv[2])};
+    const float imp = imp_of(pp, dist);
+    W.D[m] = __fdividef(c.wb_D1 * imp, 1.f - imp);
+    W.wheel[m] = k;
+    for (int j = 0; j < 3; j++) { W.n[m][j] = nn[j]; W.t1[m][j] = t1[j]; W.t2[m][j] = t2[j]; W.ra[m][j] = ra[j]; W.rb[m][j] = rb[j]; W.w[m][j] = wv[j]; }
+    W.y[m][0] = pp[2] * dot3f(nn, dv) + pp[1] * imp * (dist - pp[7]);
+    W.y[m][1] = pp[2] * dot3f(t1, dv);
+    W.y[m][2] = pp[2] * dot3f(t2, dv);
+#if defined(BRB_HOST_EMU) && defined(BRB_EMU_DEBUG)
+    printf("[wb] wheel %d dist %.6e n %.5f %.5f %.5f pos %.6f %.6f %.6f ra %.5f %.5f %.5f wv %.5f %.5f %.5f y %.4e %.4e %.4e D %.4e\n", k, dist, nn[0], nn[1], nn[2],
+           pos[0], pos[1], pos[2], ra[0], ra[1], ra[2], wv[0], wv[1], wv[2], W.y[m][0], W.y[m][1], W.y[m][2], W.D[m]);
+#endif
+  }
+}
+
+BRB_D unsigned wb_active_set(const BrbModelConsts &c, const WBSet &W, const float (&ar)[8], const float (&ab)[6], unsigned prev, float eps = 2e-4f) {
+  unsigned bits = 0;
+  const float mu = c.pp[2][0];
+  for (int k = 0; k < W.nw; k++) {
+    const float *ra = W.ra[k], *rb = W.rb[k], *wv = W.w[k];
+    const float aw = W.wheel[k] ? ar[7] : ar[6];
+    const float dx = (ab[0] + ab[4] * rb[2] - ab[5] * rb[1]) - (ar[0] + ar[4] * ra[2] - ar[5] * ra[1] + aw * wv[0]);
+    const float dy = (ab[1] + ab[5] * rb[0] - ab[3] * rb[2]) - (ar[1] + ar[5] * ra[0] - ar[3] * ra[2] + aw * wv[1]);
+    const float dz = (ab[2] + ab[3] * rb[1] - ab[4] * rb[0]) - (ar[2] + ar[3] * ra[1] - ar[4] * ra[0] + aw * wv[2]);
+    const float z0 = W.n[k][0] * dx + W.n[k][1] * dy + W.n[k][2] * dz + W.y[k][0];
+    const float z1 = mu * (W.t1[k][0] * dx + W.t1[k][1] * dy + W.t1[k][2] * dz + W.y[k][1]);
+    const float z2 = mu * (W.t2[k][0] * dx + W.t2[k][1] * dy + W.t2[k][2] * dz + W.y[k][2]);
+    const unsigned pb = prev >> (4 * k);
+    const float e0 = (pb & 1u) ? eps : -eps, e1 = (pb & 2u) ? eps : -eps, e2 = (pb & 4u) ? eps : -eps, e3 = (pb & 8u) ? eps : -eps;
+    bits |= ((unsigned)(z0 + z1 < e0) | ((unsigned)(z0 - z1 < e1) << 1) | ((unsigned)(z0 + z2 < e2) << 2) | ((unsigned)(z0 - z2 < e3) << 3)) << (4 * k);
+  }
+  return bits;
+}
+
 // ------------------------------------------------------------------------------------------------ substep driver
-struct Env03Stats { unsigned coupled, blk_contact, unsupported, fallback, csolves, coupled_last, blk_last; };
+struct Env03Stats { unsigned coupled, blk_contact, unsupported, fallback, csolves, coupled_last, blk_last, wb_last; };
 
 // gathers every contact of the substep into generic records and runs the coupled solve
 BRB_D int env03_coupled_substep(const BrbModelConsts &c, const Phys &P, const Blk &B, const float (*bpos)[3], const float *bdist,
-                                const float *bn, int nbb, float *acc) {
+                                const float *bn, int nbb, const WBSet &W, float *acc) {
   GContact gc[BRB_MAXGC];
   int n = 0;
   // wheel-floor contacts of the robot (already set up in P): frame = world axes (n = z, t1 = y, t2 = -x)
@@ -483,6 +708,13 @@ BRB_D int env03_coupled_substep(const BrbModelConsts &c, const Phys &P, const Bl
     g.y[1] = pp[2] * dot3f(g.t1, dv);
     g.y[2] = pp[2] * dot3f(g.t2, dv);
     g.robot_sign = -1; g.block_sign = 1; g.wheel = -1;
+  }
+  // wheel-block contacts: body A = robot (wheel: its column rides along), body B = block
+  for (int k2 = 0; k2 < W.nw && n < BRB_MAXGC; k2++) {
+    GContact &g = gc[n++];
+    for (int k = 0; k < 3; k++) { g.n[k] = W.n[k2][k]; g.t1[k] = W.t1[k2][k]; g.t2[k] = W.t2[k2][k]; g.ra[k] = W.ra[k2][k]; g.rb[k] = W.rb[k2][k];
+                                  g.wa[k] = W.w[k2][k]; g.y[k] = W.y[k2][k]; }
+    g.D = W.D[k2]; g.mu = c.pp[2][0]; g.robot_sign = -1; g.block_sign = 1; g.wheel = W.wheel[k2];
   }
   return env03_coupled_solve(c, P, gc, n, acc);
 }
@@ -547,12 +779,15 @@ BRB_D unsigned cb_active_set(const BrbModelConsts &c, const CBSet &Q, const floa
 // One Newton step of the coupled robot+block system on the given active sets: assemble the robot's 8x8 (H, r), the
 // block's 6x6 (Hb, rb) and the 6x6 coupling Cc from the chassis-block contacts, eliminate the block (brb_schur6.inc),
 // solve the reduced 8x8 (brb_chol8.inc), back-substitute the block.  Exact for fixed active sets (A.8).
-BRB_D void coupled_solve_fast(const BrbModelConsts &c, const Phys &P, const Blk &B, const CBSet &Q, float (&ar)[8], float (&ab)[6]) {
-  float H[36], r[8], Hb[21], rb[6], Cc[6][6];
+// WB = true additionally assembles the wheel-block contacts of W (own frame per contact, wheel column in the robot's point map, so the
+// coupling block has rows for the wheel dofs: Cc[8][6], brb_schur6w.inc); that instance is not inlined (coupled_solve_wb): rare path.
+template <bool WB>
+BRB_D void coupled_solve_impl(const BrbModelConsts &c, const Phys &P, const Blk &B, const CBSet &Q, const WBSet &W, float (&ar)[8], float (&ab)[6]) {
+  float H[36], r[8], Hb[21], rb[6], Cc[8][6];     // rows 6, 7 of Cc exist only for WB (never touched otherwise)
   phys_assemble<true>(c, P, P.valid ? P.bits : 0u, H, r);
   blk_assemble(c, B, B.bits, Hb, rb);
 #pragma unroll
-  for (int i = 0; i < 6; i++)
+  for (int i = 0; i < (WB ? 8 : 6); i++)
 #pragma unroll
     for (int j = 0; j < 6; j++) Cc[i][j] = 0.f;
   const float mu = c.pp[2][0];
@@ -621,6 +856,81 @@ BRB_D void coupled_solve_fast(const BrbModelConsts &c, const Phys &P, const Blk 
 #undef CDOT_A
 #undef CDOT_B
   }
+  if (WB) {
+    for (int k = 0; k < W.nw; k++) {
+      const unsigned b = (W.bits >> (4 * k)) & 15u;
+      if (!b) continue;
+      const float b0 = (float)(b & 1u), b1 = (float)((b >> 1) & 1u), b2 = (float)((b >> 2) & 1u), b3 = (float)((b >> 3) & 1u);
+      const float Dc = W.D[k], Dm = Dc * mu, Dmm = Dm * mu;
+      const float W00 = Dc * (b0 + b1 + b2 + b3), W01 = Dm * (b0 - b1), W02 = Dm * (b2 - b3), W11 = Dmm * (b0 + b1), W22 = Dmm * (b2 + b3);
+      const float *n = W.n[k], *t1 = W.t1[k], *t2 = W.t2[k];
+      float g0[3], g1[3], g2[3], S[3][3];
+      for (int j = 0; j < 3; j++) { g0[j] = W00 * n[j] + W01 * t1[j] + W02 * t2[j]; g1[j] = W01 * n[j] + W11 * t1[j]; g2[j] = W02 * n[j] + W22 * t2[j]; }
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) S[i][j] = n[i] * g0[j] + t1[i] * g1[j] + t2[i] * g2[j];
+      const float y0 = W.y[k][0], y1 = W.y[k][1], y2 = W.y[k][2];
+      const float u0 = W00 * y0 + W01 * y1 + W02 * y2, u1 = W01 * y0 + W11 * y1, u2 = W02 * y0 + W22 * y2;
+      float gv[3];
+      for (int j = 0; j < 3; j++) gv[j] = u0 * n[j] + u1 * t1[j] + u2 * t2[j];
+      // point maps: robot P_a = [1 | -[ra]x | wv e_kw'], block P_b = [1 | -[rb]x]; columns c_0 = (0,-z,y), c_1 = (z,0,-x), c_2 = (-y,x,0)
+      float ca[4][3], cb[3][3];          // robot: the three angular columns and the wheel column; block: the three angular columns
+      {
+        const float ax = W.ra[k][0], ay = W.ra[k][1], az = W.ra[k][2], bx = W.rb[k][0], by = W.rb[k][1], bz = W.rb[k][2];
+        ca[0][0] = 0.f; ca[0][1] = -az; ca[0][2] = ay;  ca[1][0] = az; ca[1][1] = 0.f; ca[1][2] = -ax;  ca[2][0] = -ay; ca[2][1] = ax; ca[2][2] = 0.f;
+        cb[0][0] = 0.f; cb[0][1] = -bz; cb[0][2] = by;  cb[1][0] = bz; cb[1][1] = 0.f; cb[1][2] = -bx;  cb[2][0] = -by; cb[2][1] = bx; cb[2][2] = 0.f;
+        for (int j = 0; j < 3; j++) ca[3][j] = W.w[k][j];
+      }
+      float Sa[4][3], Sb[3][3];          // S c for every non-trivial column
+      for (int q = 0; q < 4; q++)
+        for (int i = 0; i < 3; i++) Sa[q][i] = S[i][0] * ca[q][0] + S[i][1] * ca[q][1] + S[i][2] * ca[q][2];
+      for (int q = 0; q < 3; q++)
+        for (int i = 0; i < 3; i++) Sb[q][i] = S[i][0] * cb[q][0] + S[i][1] * cb[q][1] + S[i][2] * cb[q][2];
+      const bool right = W.wheel[k] != 0;
+      // robot block: + P_a' S P_a, rhs + P_a' gv   (dof order: lin 0-2, ang 3-5, wheel kw)
+      H[LT(0, 0)] += S[0][0]; H[LT(1, 0)] += S[1][0]; H[LT(2, 0)] += S[2][0]; H[LT(1, 1)] += S[1][1]; H[LT(2, 1)] += S[2][1]; H[LT(2, 2)] += S[2][2];
+      for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) H[LT(3 + i, j)] += Sa[i][j];
+        for (int j = 0; j <= i; j++) H[LT(3 + i, 3 + j)] += dot3f(ca[i], Sa[j]);
+        r[i] += gv[i];
+        r[3 + i] += dot3f(ca[i], gv);
+      }
+      {
+        float hw[7];
+        for (int j = 0; j < 3; j++) { hw[j] = Sa[3][j]; hw[3 + j] = dot3f(ca[j], Sa[3]); }
+        hw[6] = dot3f(ca[3], Sa[3]);
+        const float rw = dot3f(ca[3], gv);
+        if (right) { for (int j = 0; j < 6; j++) H[LT(7, j)] += hw[j]; H[LT(7, 7)] += hw[6]; r[7] += rw; }
+        else { for (int j = 0; j < 6; j++) H[LT(6, j)] += hw[j]; H[LT(6, 6)] += hw[6]; r[6] += rw; }
+      }
+      // block: + P_b' S P_b, rhs - P_b' gv
+      Hb[LT6(0, 0)] += S[0][0]; Hb[LT6(1, 0)] += S[1][0]; Hb[LT6(2, 0)] += S[2][0]; Hb[LT6(1, 1)] += S[1][1]; Hb[LT6(2, 1)] += S[2][1]; Hb[LT6(2, 2)] += S[2][2];
+      for (int i = 0; i < 3; i++) {
+        for (int j = 0; j < 3; j++) Hb[LT6(3 + i, j)] += Sb[i][j];
+        for (int j = 0; j <= i; j++) Hb[LT6(3 + i, 3 + j)] += dot3f(cb[i], Sb[j]);
+        rb[i] -= gv[i];
+        rb[3 + i] -= dot3f(cb[i], gv);
+      }
+      // coupling: Cc[robot dof][block dof] = -(P_a' S P_b)
+      for (int i = 0; i < 3; i++)
+        for (int j = 0; j < 3; j++) {
+          Cc[i][j] -= S[i][j];
+          Cc[i][3 + j] -= Sb[j][i];
+          Cc[3 + i][j] -= Sa[i][j];
+          Cc[3 + i][3 + j] -= dot3f(ca[i], Sb[j]);
+        }
+      for (int j = 0; j < 3; j++) {
+        const float cl = Sa[3][j], cg = dot3f(ca[3], Sb[j]);
+        if (right) { Cc[7][j] -= cl; Cc[7][3 + j] -= cg; } else { Cc[6][j] -= cl; Cc[6][3 + j] -= cg; }
+      }
+    }
+#define BRB_SCHUR6_ELIMINATE
+#include "brb_schur6w.inc"
+#undef BRB_SCHUR6_ELIMINATE
+#include "brb_chol8.inc"
+#define BRB_SCHUR6_BACKSUB
+#include "brb_schur6w.inc"
+#undef BRB_SCHUR6_BACKSUB
+  } else {
 #define BRB_SCHUR6_ELIMINATE
 #include "brb_schur6.inc"
 #undef BRB_SCHUR6_ELIMINATE
@@ -628,10 +938,22 @@ BRB_D void coupled_solve_fast(const BrbModelConsts &c, const Phys &P, const Blk 
 #define BRB_SCHUR6_BACKSUB
 #include "brb_schur6.inc"
 #undef BRB_SCHUR6_BACKSUB
+  }
 #pragma unroll
   for (int k = 0; k < 8; k++) ar[k] = r[k];
 #pragma unroll
   for (int k = 0; k < 6; k++) ab[k] = rb[k];
+}
+BRB_D void coupled_solve_fast(const BrbModelConsts &c, const Phys &P, const Blk &B, const CBSet &Q, const WBSet &W, float (&ar)[8], float (&ab)[6]) {
+  coupled_solve_impl<false>(c, P, B, Q, W, ar, ab);
+}
+#ifdef BRB_HOST_EMU
+static __attribute__((noinline))
+#else
+__device__ __noinline__
+#endif
+void coupled_solve_wb(const BrbModelConsts &c, const Phys &P, const Blk &B, const CBSet &Q, const WBSet &W, float (&ar)[8], float (&ab)[6]) {
+  coupled_solve_impl<true>(c, P, B, Q, W, ar, ab);
 }
 
 // does the block touch the chassis box this substep?  bounding spheres first, then the SAT collider
@@ -665,6 +987,9 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
   float bpos[8][3], bdist[8], bn[3];
   CBSet Q;
   Q.nc = 0; Q.bits = 0xFFFFFFFFu;
+  WBSet W;
+  W.nw = 0; W.bits = 0xFFu;
+  int wprev_nw = -1;
   unsigned was = 0u;
   int wasn = -1;
   for (;;) {
@@ -685,7 +1010,15 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
         if (Q.nc != qprev_nc) Q.bits = 0xFFFFFFFFu;
         if (Q.nc > 0) es.coupled++;
       }
-      es.coupled_last = (unsigned)Q.nc;
+      wb_setup(c, P, B, W);
+      if (W.nw != wprev_nw) W.bits = 0xFFu;
+      if (W.nw > 0 && Q.nc == 0) es.coupled++;
+      wprev_nw = W.nw;
+      es.coupled_last = (unsigned)(Q.nc + W.nw);
+      es.wb_last = W.near ? 1u : 0u;
+#ifdef BRB_PROBE_WB      // kernel-tuning experiment: count narrow-phase calls in the block-contact statistic
+      if (W.near) es.blk_contact += 1000u;
+#endif
       es.blk_last = B.nc > 0 ? 1u : 0u;
       qprev_nc = Q.nc;
       was = P.valid; wasn = B.nc;
@@ -706,22 +1039,24 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
 #endif
     if (ctasync) BRB_CTA_SYNC(); else __syncwarp(wmask);
     if (done) {
-    } else if (P.valid || B.nc > 0 || Q.nc > 0) {
-      coupled_solve_fast(c, P, B, Q, ar, ab);
+    } else if (P.valid || B.nc > 0 || Q.nc > 0 || W.nw > 0) {
+      if (W.nw > 0) coupled_solve_wb(c, P, B, Q, W, ar, ab);
+      else coupled_solve_fast(c, P, B, Q, W, ar, ab);
       es.csolves++;
       // rows within eps of their switching surface keep their state; when the undamped iteration starts to cycle the band
       // is widened (x4 per extra solve from the third on), which freezes the flapping rows at a force error <= D eps
       const float eps = it < 2 ? 2e-4f : (it == 2 ? 8e-4f : (it == 3 ? 3.2e-3f : (it == 4 ? 1.28e-2f : 5.12e-2f)));
       const unsigned nr = P.valid ? phys_active_set<true>(c, P, ar, P.bits, eps) : P.bits;
       const unsigned nbl = blk_active_set(c, B, ab, B.bits, eps), nq = cb_active_set(c, Q, ar, ab, Q.bits, eps);
-      conv = (nr == P.bits) && (nbl == B.bits) && (nq == Q.bits);
-      P.bits = nr; B.bits = nbl; Q.bits = nq;
+      const unsigned nwb = W.nw > 0 ? wb_active_set(c, W, ar, ab, W.bits, eps) : W.bits;
+      conv = (nr == P.bits) && (nbl == B.bits) && (nq == Q.bits) && (nwb == W.bits);
+      P.bits = nr; B.bits = nbl; Q.bits = nq; W.bits = nwb;
       if (!conv && ++it >= 7) {
         // the undamped active-set iteration is cycling: finish with the line-search Newton, and seed the next substep with
         // the active sets of ITS solution (otherwise the same cycle — and the same fallback — repeats substep after substep)
         float acc[14];
         es.fallback++;
-        if (env03_coupled_substep(c, P, B, bpos, bdist, bn, Q.nc > 0 ? nbb : 0, acc)) P.n_nonconv++;
+        if (env03_coupled_substep(c, P, B, bpos, bdist, bn, Q.nc > 0 ? nbb : 0, W, acc)) P.n_nonconv++;
 #pragma unroll
         for (int k = 0; k < 8; k++) ar[k] = acc[k];
 #pragma unroll
@@ -729,6 +1064,7 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
         if (P.valid) P.bits = phys_active_set<true>(c, P, ar, P.bits);
         B.bits = blk_active_set(c, B, ab, B.bits);
         Q.bits = cb_active_set(c, Q, ar, ab, Q.bits);
+        if (W.nw > 0) W.bits = wb_active_set(c, W, ar, ab, W.bits);
         conv = true;
       }
     } else {
@@ -878,7 +1214,7 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
   }
   KF qprev[4];
   float pstale[3];
-  Env03Stats es = {0u, 0u, 0u, 0u, 0u, 0u, 0u};
+  Env03Stats es = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
   phys03_run<BRB_MAXIT>(c, st, B, c.frame_skip, qprev, pstale, es, wmask, ctasync);
   stat[0] = c.frame_skip; stat[1] = st.n_contact; stat[2] = st.n_solve; stat[3] = st.n_nonconv; stat[7] = st.n_slots;
   stat[8] = es.coupled; stat[9] = es.blk_contact; stat[10] = es.fallback; stat[11] = es.csolves;
@@ -888,8 +1224,11 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
     // robots whose block was touching the chassis in the last substep (impacts last ~6 env steps) get their own bucket, so
     // the warps running the coupled assembly are not diluted by robots on the uncoupled path
     // (one bucket per contact count class: the coupled assembly loops over the contacts, lanes with fewer of them idle)
-    if (es.coupled_last) stat[6] = BRB_NGROUPS - 3 + (es.coupled_last <= 2u ? 0u : (es.coupled_last <= 4u ? 1u : 2u));
-    else if (es.blk_last) stat[6] = BRB_NGROUPS - 4;      // block resting / sliding on the floor: its floor contacts are a rare path
+    if (es.coupled_last) stat[6] = BRB_NGROUPS - 4 + (es.coupled_last <= 2u ? 0u : (es.coupled_last <= 4u ? 1u : 2u));
+    else if (es.blk_last) stat[6] = BRB_NGROUPS - 5;      // block resting / sliding on the floor: its floor contacts are a rare path
+    // a wheel within reach of the block runs the cylinder-box collider (and, in contact, the not-inlined solve with wheel rows) every
+    // substep: in lockstep one such robot holds up its CTA, so they get CTAs of their own, visited first
+    if (es.wb_last) stat[6] = BRB_NGROUPS - 1;
   }
 
   double qpos[16];
@@ -970,6 +1309,7 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
       }
       near_wheel = near_wheel || !sep;
     }
+    if (c.flags & BRB_FLAG_WHEEL_BLOCK) near_wheel = false;     // the pair is generated (wb_setup): nothing unsupported about it
 #ifdef BRB_PROBE_UNSUP   // kernel-tuning experiment: count one cause at a time (1 = chassis-floor, 2 = wheel flat, 4 = wheel near block)
     stat[4] = (((BRB_PROBE_UNSUP & 1) && low <= 0.0) || ((BRB_PROBE_UNSUP & 2) && tri <= 0.0) || ((BRB_PROBE_UNSUP & 4) && near_wheel)) ? 1u : 0u;
 #else

@@ -43,8 +43,8 @@ struct BrbState {
 // env (0 = far airborne, then by landing time, then by wheel-rim contact pattern) plus a histogram; brb_group_kernel counting-sorts them into the
 // next launch's order, so that the lanes of a warp mostly run the same contact path.
 #define BRB_NLAND 8        // landing-time bins of airborne robots that will touch down during the next step
-#define BRB_NCOUPLED 4     // Env03-v2: robots whose block lies on the floor, then those whose block touches the chassis by
-                           // number of chassis-block contacts (1-2, 3-4, 5-8)
+#define BRB_NCOUPLED 5     // Env03-v2: robots whose block lies on the floor, then those whose block touches the chassis by
+                           // number of chassis-block contacts (1-2, 3-4, 5-8), then (highest key, visited first) those with a wheel within reach of the block
 #define BRB_NGROUPS (1 + BRB_NLAND + 16 + BRB_NCOUPLED)   // 0 = stays airborne, 1..NLAND = landing, then NLAND + rank of the
                                                           // contact-slot pattern (1..15), then the coupled buckets (<= 31 keys in all)
 struct BrbPerm {

@@ -55,7 +55,7 @@ class BrbModelConsts(C.Structure):
         ("blk_half", C.c_float), ("blk_mass", C.c_float), ("blk_inertia", C.c_float), ("blk_radius", C.c_float),
         ("chassis_radius", C.c_float),
         ("geo_lo", C.c_float * 4),
-        ("nq", C.c_int), ("nv", C.c_int), ("reserved", C.c_int),
+        ("nq", C.c_int), ("nv", C.c_int), ("wb_D1", C.c_float),
     ]
 
 
@@ -82,7 +82,7 @@ def _skew(v):
 
 
 def compile_model(spec: ModelSpec, env_kind: int, max_episode_steps: int, frame_skip: int = 250,
-                  actderiv_skip_clamped: bool = True, truncate_unsupported: bool = False) -> RobotModel:
+                  actderiv_skip_clamped: bool = True, truncate_unsupported: bool = False, wheel_block: bool = False) -> RobotModel:
     # ---- class checks ------------------------------------------------------------------------
     free_roots = [b for b in range(1, len(spec.bodies)) if spec.bodies[b].joint >= 0
                   and spec.joints[spec.bodies[b].joint].type == JNT_FREE]
@@ -286,11 +286,19 @@ def compile_model(spec: ModelSpec, env_kind: int, max_episode_steps: int, frame_
         fid, bid_, cid = gid[id(floor)], gid[id(bgeoms[0])], gid[id(chassis_geoms[0])]
         by_geoms = {frozenset((p.geom1, p.geom2)): p for p in spec.pairs}
         c.pp[1][:] = pair_params(by_geoms[frozenset((fid, bid_))], invw[bb.name][0])
-        c.pp[2][:] = pair_params(by_geoms[frozenset((cid, bid_))], invw[cb.name][0] + invw[bb.name][0])
+        cbpp = pair_params(by_geoms[frozenset((cid, bid_))], invw[cb.name][0] + invw[bb.name][0])
+        c.pp[2][:] = cbpp
+        # wheel-block pairs: same mixed solref / solimp / margin / friction as chassis-block (checked), own diagonal approximation
+        wgeoms = [g for g in spec.geoms if g.body in wheels]
+        wpp = [pair_params(by_geoms[frozenset((gid[id(g)], bid_))], invw[spec.bodies[g.body].name][0] + invw[bb.name][0]) for g in wgeoms]
+        if len(wpp) != 2 or any(abs(a - b) > 1e-12 * max(1.0, abs(b)) for w_ in wpp for a, b in zip(w_[:3] + w_[4:], cbpp[:3] + cbpp[4:])) \
+                or abs(wpp[0][3] - wpp[1][3]) > 1e-9 * abs(wpp[0][3]):
+            raise UnsupportedModel("wheel-block pairs must share the chassis-block contact parameters")
+        c.wb_D1 = wpp[0][3]
         hb = bgeoms[0].size[0]
         c.blk_half, c.blk_mass, c.blk_inertia, c.blk_radius = hb, bb.mass, Ib[0, 0], hb * math.sqrt(3.0)
         c.chassis_radius = float(np.linalg.norm(chassis_geoms[0].size))
-    c.flags = (1 if actderiv_skip_clamped else 0) | (2 if truncate_unsupported else 0)     # include/brb.h BRB_FLAG_*
+    c.flags = (1 if actderiv_skip_clamped else 0) | (2 if truncate_unsupported else 0) | (4 if wheel_block else 0)     # include/brb.h BRB_FLAG_*
 
     # MuJoCo accumulates data.time += h once per substep in fp64; reproduce the exact sequence
     # (np.cumsum adds sequentially, left to right, exactly like the C loop `time += h`)

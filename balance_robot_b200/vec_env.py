@@ -144,7 +144,8 @@ class BalanceVecEnv:
     metadata = {"render_modes": ["rgb_array"], "render_fps": 200}   # RobotBaseEnv.py:30-37 (no renderer here)
 
     def __init__(self, env_id: str, num_envs: int, device="cuda:0", seed: int = 0, env_id_offset: int = 0,
-                 output: str = "torch", actderiv_skip_clamped: bool = True, truncate_unsupported: bool = False):
+                 output: str = "torch", actderiv_skip_clamped: bool = True, truncate_unsupported: bool = False,
+                 wheel_block: bool = False):
         if output not in ("torch", "numpy"):
             raise ValueError("output must be 'torch' or 'numpy'")
         self.spec = registry.spec(env_id)
@@ -158,7 +159,8 @@ class BalanceVecEnv:
         self.observation_space, self.action_space = OBSERVATION_SPACE, ACTION_SPACE
         self.render_mode = None
         self.robot = model_mod.compile_model(mjcf.parse(self.spec.scene), self.spec.kind, self.spec.max_episode_steps,
-                                             actderiv_skip_clamped=actderiv_skip_clamped, truncate_unsupported=truncate_unsupported)
+                                             actderiv_skip_clamped=actderiv_skip_clamped, truncate_unsupported=truncate_unsupported,
+                                             wheel_block=wheel_block)
         L = _cabi.lib()
         dev_index = self.device.index if self.device.index is not None else torch.cuda.current_device()
         self._model = C.c_void_p()

@@ -35,6 +35,10 @@ extern "C" {
  * generate (BRB_STAT_UNSUPPORTED) is ended as TRUNCATED (TimeLimit.truncated = True, so a trainer bootstraps the value) and
  * auto-reset, instead of stepping on with those contacts missing. */
 #define BRB_FLAG_TRUNCATE_UNSUPPORTED 2
+/* Env03-v2, opt-in: generate wheel-block contacts (own analytic cylinder-box collider, brb_env03.cuh).  Off (default) = no contact for
+ * that pair, poses within reach are counted as unsupported.  On costs ~2.3x step time at 65,536 robots with random actions: the
+ * narrow phase and the solve with wheel rows are rare divergent paths inside CTAs that walk the substep loop in lockstep. */
+#define BRB_FLAG_WHEEL_BLOCK 4
 
 #define BRB_NSTATS 12
 #define BRB_STAT_SUBSTEPS 0          /* env-substeps executed */
@@ -69,7 +73,8 @@ typedef struct BrbModelConsts {
   float pp[3][8];
   float blk_half, blk_mass, blk_inertia, blk_radius, chassis_radius;
   float geo_lo[4]; /* fp64 - fp32 residuals of ox, oz, rad, hl: the contact on/off predicate is re-evaluated in fp64 near dist = 0 */
-  int nq, nv, reserved;
+  int nq, nv;
+  float wb_D1;     /* Env03-v2: row-weight scale D1 of the wheel-block pair (its other parameters equal the chassis-block pair's pp[2]) */
 } BrbModelConsts;
 
 typedef struct BrbModel BrbModel;

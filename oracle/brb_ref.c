@@ -507,6 +507,139 @@ static void collide_box_box(const BrbRefModel *m, BrbRefData *d, int pair) {
   }
 }
 
+/* cylinder-box (Env03-v2: wheel vs block).  MuJoCo 3.2.0 sends this pair to libccd's MPR through mjc_Convex: an iterative portal
+ * refinement whose result on a curved feature is only good to its tolerance (1e-6 m of support distance, i.e. about 1 % of normal
+ * direction on the 34 mm wheel).  It is NOT restated.  Own analytic collider, same contact class (one point, normal from geom1 to
+ * geom2, position midway between the surfaces):
+ *   sep(d) = d.(c2 - c1) - h_cyl(d) - h_box(d)  is a lower bound of the signed distance for every unit d (support functions), and
+ *   the signed distance is its maximum.  It is evaluated on the directions at which the maximum can sit for these two shapes:
+ *   box face normals (3), the cylinder axis, axis x box edge (3: edge against the curved side), the radial direction to each box vertex
+ *   (8: vertex against the curved side), the direction from the nearest rim point of either cap to each vertex (16), and for each box
+ *   edge direction the best direction perpendicular to it (edge against a rim circle: a one-dimensional search, see below).  The contact point comes from two alternating projections between the
+ *   support feature of the box and of the cylinder along the chosen direction. */
+static double cyl_box_sep(const double *dir, const double *delta, const double *a, double R, double L, const double E[3][3], const double *h) {
+  double da = dot3(dir, a), s = dot3(dir, delta) - L * fabs(da) - R * sqrt(fmax(0.0, 1.0 - da * da));
+  for (int j = 0; j < 3; j++) s -= h[j] * fabs(dot3(dir, E[j]));
+  return s;
+}
+#define CYLBOX_TAU 0.02
+static double soft_sign(double x) { return fmax(-1.0, fmin(1.0, x / CYLBOX_TAU)); }
+/* cos(2 pi k / 16); sin(x) = cos(x - pi/2) = entry (k + 12) & 15 */
+static const double CYLBOX_COS16[16] = {1.0, 0.92387953251128674, 0.70710678118654752, 0.38268343236508977, 0.0, -0.38268343236508977,
+                                        -0.70710678118654752, -0.92387953251128674, -1.0, -0.92387953251128674, -0.70710678118654752,
+                                        -0.38268343236508977, 0.0, 0.38268343236508977, 0.70710678118654752, 0.92387953251128674};
+static double cyl_box_g(double c, double s, double D1, double D2, double A1, double A2, double R, double L, double h1, double h2) {
+  const double da = A1 * c + A2 * s;
+  return D1 * c + D2 * s - L * fabs(da) - R * sqrt(fmax(0.0, 1.0 - da * da)) - h1 * fabs(c) - h2 * fabs(s);
+}
+/* candidate direction v (any length; `orient`: flip it towards the box centre first): keeps the direction of the largest separation */
+static void cyl_box_try(const double *v, int orient, const double *delta, const double *a, double R, double L, const double E[3][3],
+                        const double *h, double *best, double *bd) {
+  double n2 = dot3(v, v);
+  if (n2 <= 1e-16) return;
+  double in = 1.0 / sqrt(n2);
+  if (orient && dot3(v, delta) < 0) in = -in;
+  double t[3] = {v[0] * in, v[1] * in, v[2] * in}, s = cyl_box_sep(t, delta, a, R, L, E, h);
+  if (s > *best) { *best = s; bd[0] = t[0]; bd[1] = t[1]; bd[2] = t[2]; }
+}
+
+/* returns 1 and fills dist / normal / pos when the shapes are within `margin`; exposed for tests */
+int brb_ref_cylinder_box(const double c[3], const double a_in[3], double R, double L, const double b[3], const double Emat[9] /* rows = box axes */,
+                         const double h[3], double margin, double *dist, double normal[3], double pos[3]) {
+  double a[3] = {a_in[0], a_in[1], a_in[2]}, E[3][3], delta[3] = {b[0] - c[0], b[1] - c[1], b[2] - c[2]};
+  normalize3(a);
+  for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) E[i][k] = Emat[3 * i + k];
+  double best = -1e30, bd[3] = {0, 0, 1};
+  for (int i = 0; i < 3; i++) cyl_box_try(E[i], 1, delta, a, R, L, E, h, &best, bd);
+  cyl_box_try(a, 1, delta, a, R, L, E, h, &best, bd);
+  for (int i = 0; i < 3; i++) { double x[3]; cross3(x, a, E[i]); if (dot3(x, x) > 1e-10) cyl_box_try(x, 1, delta, a, R, L, E, h, &best, bd); }
+  for (int vi = 0; vi < 8; vi++) {
+    double u[3];
+    for (int k = 0; k < 3; k++) u[k] = delta[k] + ((vi & 1) ? h[0] : -h[0]) * E[0][k] + ((vi & 2) ? h[1] : -h[1]) * E[1][k] + ((vi & 4) ? h[2] : -h[2]) * E[2][k];
+    double ua = dot3(u, a), up[3] = {u[0] - ua * a[0], u[1] - ua * a[1], u[2] - ua * a[2]};
+    double rho2 = dot3(up, up);
+    if (rho2 <= 1e-16) continue;
+    /* vertex against the curved side: radial direction (no re-orientation: it points from the axis to the vertex) */
+    cyl_box_try(up, 0, delta, a, R, L, E, h, &best, bd);
+    /* vertex against the rim of either cap: from the nearest rim point to the vertex */
+    for (int cap = 0; cap < 2; cap++) {
+      double sg = cap ? -1.0 : 1.0, ir = R / sqrt(rho2), t[3];
+      for (int k = 0; k < 3; k++) t[k] = u[k] - sg * L * a[k] - up[k] * ir;
+      cyl_box_try(t, 0, delta, a, R, L, E, h, &best, bd);
+    }
+  }
+  /* box EDGE against a rim (or the curved side, or a cap): the separating direction is perpendicular to the edge, d(phi) = cos(phi) E_a1 +
+   * sin(phi) E_a2 for an edge along E_ax.  In that plane sep is the one-dimensional function
+   *   g(phi) = D1 c + D2 s - L |A1 c + A2 s| - R sqrt(1 - (A1 c + A2 s)^2) - h1 |c| - h2 |s|        (all four parallel edges and both caps at once)
+   * which is maximised by a 16-point scan followed by a golden-section search with a fixed number of steps inside the best cell
+   * (parametrised by the tangent of the offset, so no trigonometry per step). */
+  for (int ax = 0; ax < 3; ax++) {
+    const int a1 = (ax + 1) % 3, a2 = (ax + 2) % 3;
+    const double D1 = dot3(E[a1], delta), D2 = dot3(E[a2], delta), A1 = dot3(E[a1], a), A2 = dot3(E[a2], a);
+    int kb = 0;
+    double gb = -1e30;
+    for (int k = 0; k < 16; k++) {
+      const double g = cyl_box_g(CYLBOX_COS16[k], CYLBOX_COS16[(k + 12) & 15], D1, D2, A1, A2, R, L, h[a1], h[a2]);
+      if (g > gb) { gb = g; kb = k; }
+    }
+    const double ck = CYLBOX_COS16[kb], sk = CYLBOX_COS16[(kb + 12) & 15], tmax = 0.41421356237309503 /* tan(pi/8) */, gr = 0.6180339887498949;
+    double lo = -tmax, hi = tmax, x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo), f1 = 0, f2 = 0;
+    int fresh = 2;
+    for (int it = 0; it < 14; it++) {
+      for (int w = 0; w < 2; w++) {
+        if (fresh != 2 && w != fresh) continue;
+        const double t = w ? x2 : x1, in = 1.0 / sqrt(1.0 + t * t);
+        const double g = cyl_box_g((ck - t * sk) * in, (sk + t * ck) * in, D1, D2, A1, A2, R, L, h[a1], h[a2]);
+        if (w) f2 = g; else f1 = g;
+      }
+      if (f1 > f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); fresh = 0; }
+      else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); fresh = 1; }
+    }
+    const double t = 0.5 * (lo + hi), in = 1.0 / sqrt(1.0 + t * t), cf = (ck - t * sk) * in, sf = (sk + t * ck) * in;
+    double tdir[3];
+    for (int k = 0; k < 3; k++) tdir[k] = cf * E[a1][k] + sf * E[a2][k];
+    cyl_box_try(tdir, 0, delta, a, R, L, E, h, &best, bd);
+  }
+  if (best > margin) return 0;
+  /* Contact point: support features of the two shapes along bd, refined by two alternating projections.  A feature is "selected" by
+   * the sign of bd along an axis; within CYLBOX_TAU (0.02 rad) of perpendicular the selection is blended linearly with the free
+   * coordinate (the projection of the other shape's point), so the point moves continuously from the middle of a flat-on-flat patch
+   * to its deeper end as the shapes tilt instead of jumping with the sign of a 1e-6 rad tilt. */
+  double sa = soft_sign(dot3(bd, a)), sb[3], dp[3], rdir[3] = {0, 0, 0}, wr = 0.0;
+  for (int j = 0; j < 3; j++) sb[j] = soft_sign(dot3(bd, E[j]));
+  { double da = dot3(bd, a); for (int k = 0; k < 3; k++) dp[k] = bd[k] - da * a[k]; double pm = sqrt(dot3(dp, dp));
+    if (pm > 1e-12) { for (int k = 0; k < 3; k++) rdir[k] = dp[k] / pm; wr = fmin(1.0, pm / CYLBOX_TAU); } }
+  double pc[3], qb[3];
+  for (int k = 0; k < 3; k++) pc[k] = c[k] + sa * L * a[k] + wr * R * rdir[k];
+  for (int pass = 0; pass < 2; pass++) {
+    for (int k = 0; k < 3; k++) qb[k] = b[k];
+    for (int j = 0; j < 3; j++) {
+      double rel[3] = {pc[0] - b[0], pc[1] - b[1], pc[2] - b[2]};
+      double l = -sb[j] * h[j] + (1.0 - fabs(sb[j])) * fmax(-h[j], fmin(h[j], dot3(rel, E[j])));
+      for (int k = 0; k < 3; k++) qb[k] += l * E[j][k];
+    }
+    double rel[3] = {qb[0] - c[0], qb[1] - c[1], qb[2] - c[2]}, ta = dot3(rel, a);
+    double t = sa * L + (1.0 - fabs(sa)) * fmax(-L, fmin(L, ta));
+    double rv[3];
+    for (int k = 0; k < 3; k++) rv[k] = rel[k] - ta * a[k];                /* radial part of the box point, inside the disc */
+    { double n2 = dot3(rv, rv); if (n2 > R * R) { double in = R / sqrt(n2); for (int k = 0; k < 3; k++) rv[k] *= in; } }
+    for (int k = 0; k < 3; k++) pc[k] = c[k] + t * a[k] + wr * R * rdir[k] + (1.0 - wr) * rv[k];
+  }
+  *dist = best;
+  for (int k = 0; k < 3; k++) { normal[k] = bd[k]; pos[k] = 0.5 * (pc[k] + qb[k]); }
+  return 1;
+}
+
+static void collide_cylinder_box(const BrbRefModel *m, BrbRefData *d, int pair) {
+  int g1 = m->pair_geom1[pair], g2 = m->pair_geom2[pair];
+  const double *R1 = d->geom_xmat[g1], *R2 = d->geom_xmat[g2];
+  double a[3] = {R1[2], R1[5], R1[8]}, E[9], dist, n[3], pos[3];
+  for (int i = 0; i < 3; i++) for (int k = 0; k < 3; k++) E[3 * i + k] = R2[3 * k + i];
+  if (brb_ref_cylinder_box(d->geom_xpos[g1], a, m->geom_size[g1][0], m->geom_size[g1][1], d->geom_xpos[g2], E, m->geom_size[g2],
+                           m->pair_margin[pair], &dist, n, pos))
+    new_contact(d, m, pair, dist, pos, n);
+}
+
 static void make_frame(double *f) { /* mju_makeFrame with an undefined y axis */
   normalize3(f);
   f[3] = f[4] = f[5] = 0;
@@ -524,7 +657,7 @@ static void collision(const BrbRefModel *m, BrbRefData *d) {
     if (t1 == BRB_GEOM_PLANE && t2 == BRB_GEOM_CYLINDER) collide_plane_cylinder(m, d, p);
     else if (t1 == BRB_GEOM_PLANE && t2 == BRB_GEOM_BOX) collide_plane_box(m, d, p);
     else if (t1 == BRB_GEOM_BOX && t2 == BRB_GEOM_BOX) collide_box_box(m, d, p);
-    /* cylinder-box (wheel vs Env03 block; MuJoCo: libccd MPR) is not restated: such pairs produce no contacts here */
+    else if (t1 == BRB_GEOM_CYLINDER && t2 == BRB_GEOM_BOX && (m->flags & BRB_FLAG_CYLINDER_BOX)) collide_cylinder_box(m, d, p);
   }
   for (int i = 0; i < d->ncon; i++) make_frame(d->contact[i].frame);
 }

@@ -42,6 +42,7 @@ extern "C" {
 /* flags */
 #define BRB_FLAG_ACTDERIV_SKIP_CLAMPED 1 /* A.9: no actuator velocity derivative while on forcerange */
 #define BRB_FLAG_RPY_FROM_FIRST_ROW 2    /* A.7: R_py = 2 mu^2 R(first pyramid row) */
+#define BRB_FLAG_CYLINDER_BOX 4          /* wheel-block contacts through the own analytic cylinder-box collider (brb_ref.c) */
 
 typedef struct BrbRefModel {
   int nq, nv, nu, nbody, njnt, ngeom, npair, flags;
@@ -110,6 +111,9 @@ void brb_ref_kinematics(const BrbRefModel *m, BrbRefData *d);
 void brb_ref_mass_matrix(const BrbRefModel *m, BrbRefData *d);
 void brb_ref_bias(const BrbRefModel *m, BrbRefData *d);
 double brb_ref_energy(const BrbRefModel *m, BrbRefData *d, double *kinetic, double *potential);
+/* own analytic cylinder-box collider (see brb_ref.c): 1 + dist / normal (cylinder -> box) / pos when within margin */
+int brb_ref_cylinder_box(const double c[3], const double axis[3], double R, double L, const double b[3], const double E_rows[9],
+                         const double h[3], double margin, double *dist, double normal[3], double pos[3]);
 /* point Jacobian of body b at world point p: jacp, jacr are 3 x nv row-major (either may be NULL) */
 void brb_ref_jac(const BrbRefModel *m, const BrbRefData *d, int body, const double p[3], double *jacp, double *jacr);
 

@@ -16,6 +16,7 @@ LIB_PATH = HERE / "libbrb_ref.so"
 
 MAXBODY, MAXJNT, MAXNQ, MAXNV, MAXGEOM, MAXPAIR, MAXU, MAXCON, MAXEFC = 6, 6, 20, 16, 8, 16, 4, 32, 128
 FLAG_ACTDERIV_SKIP_CLAMPED, FLAG_RPY_FROM_FIRST_ROW = 1, 2
+FLAG_CYLINDER_BOX = 4            # wheel-block contacts through the own analytic cylinder-box collider (brb_ref.c)
 ENV_KINDS = {"Env01-v1": 0, "Env01-v2": 1, "Env01-v3": 2, "Env03-v2": 3}
 
 d, i = C.c_double, C.c_int

@@ -101,3 +101,10 @@ extern "C" void emu_set_state(Emu *e, const double *qpos, const double *qvel) {
   }
 }
 extern "C" void emu_get_stats(Emu *e, unsigned long long *out) { memcpy(out, e->stats, sizeof e->stats); }
+
+// test hook: the fp32 cylinder-box collider of brb_env03.cuh on its own (tests/test_env03_parity.py compares it with the oracle's)
+extern "C" int emu_cyl_box(const float *c, const float *a, float R, float L, const float *b, const float *E_rows, float h, float margin,
+                           float *dist, float *nrm, float *pos) {
+  const float E[3][3] = {{E_rows[0], E_rows[1], E_rows[2]}, {E_rows[3], E_rows[4], E_rows[5]}, {E_rows[6], E_rows[7], E_rows[8]}};
+  return env03_cyl_box(c, a, R, L, b, E, h, margin, dist, nrm, pos);
+}

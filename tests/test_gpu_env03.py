@@ -8,7 +8,7 @@ import helpers
 import parity_checks as pc
 from balance_robot_b200 import make_vec, mjcf, model
 from oracle import ref
-from test_env03_parity import check_task_outputs, env03_single_step
+from test_env03_parity import check_task_outputs, env03_single_step, wheel_block_scenario
 from test_gpu_parity import GpuAdapter
 
 pytestmark = pytest.mark.gpu
@@ -84,7 +84,7 @@ def test_truncate_unsupported_flag_ends_the_episode_instead_of_stepping_on():
     """BRB_FLAG_TRUNCATE_UNSUPPORTED (opt-in): a robot whose wheel comes within reach of the block -- a pair the kernels generate
     no contact for -- is ended as truncated and reset; with the flag off (default, the reference's semantics) it is only counted."""
     n, steps = 16384, 150
-    on = make_vec("Env03-v2", n, seed=1, truncate_unsupported=True)
+    on = make_vec("Env03-v2", n, seed=1, truncate_unsupported=True)      # wheel-block pair not generated (default): within reach = unsupported
     off = make_vec("Env03-v2", n, seed=1)
     on.reset(); off.reset()
     gen = torch.Generator(device="cuda").manual_seed(5)
@@ -99,3 +99,26 @@ def test_truncate_unsupported_flag_ends_the_episode_instead_of_stepping_on():
     assert u_off > 0 and u_on > 0
     assert 0.5 * u_on <= cuts <= u_on, (cuts, u_on)                     # a flagged step that also terminated (pitch) is not "truncated"
     on.close(); off.close()
+
+
+def test_wheel_block_contacts_match_oracle_on_the_device():
+    """Same adversarial set-up as tests/test_env03_parity.py::test_wheel_block_contacts_match_oracle, through the C-ABI; and a soak with the
+    pair generated: nothing is counted as unsupported any more."""
+    n, seed = 24, 17
+    env = GpuAdapter("Env03-v2", n, seed, wheel_block=True)
+    rv = ref.RefVecEnv(mjcf.parse("scene_env03.xml"), "Env03-v2", n, 1200, nthreads=8,
+                       flags=ref.FLAG_ACTDERIV_SKIP_CLAMPED | ref.FLAG_RPY_FROM_FIRST_ROW | ref.FLAG_CYLINDER_BOX)
+    rv.set_attack_side(ref.env03_attack_side(seed, 0, n))
+    er, eb, contacts = wheel_block_scenario(env, rv, n, seed, 8)
+    assert contacts >= 5 * n
+    assert np.median(er) < 2e-6 and np.quantile(er, 0.80) < 1e-5 and (er >= 1e-3).mean() <= 0.04, (np.quantile(er, [0.5, 0.8, 0.95]), er.max())
+    assert np.median(eb) < 5e-6 and np.quantile(eb, 0.75) < 1e-5 and (eb >= 1e-3).mean() <= 0.07, (np.quantile(eb, [0.5, 0.75, 0.95]), eb.max())
+    env.close(); rv.close()
+    big = make_vec("Env03-v2", 16384, seed=2, wheel_block=True)
+    big.reset()
+    gen = torch.Generator(device="cuda").manual_seed(3)
+    for _ in range(300):
+        obs, r, d, info = big.step(torch.rand((16384, 2), device="cuda", generator=gen) * 2 - 1)
+    st = big.stats()
+    assert torch.isfinite(obs).all() and st["unsupported"] == 0 and st["nonconverged"] < 1e-4 * st["substeps"], st
+    big.close()
