@@ -585,7 +585,6 @@ struct WBSet {
 BRB_D void wb_setup(const BrbModelConsts &c, const Phys &P, const Blk &B, WBSet &W) {
   W.nw = 0;
   W.near = false;
-  if (!(c.flags & BRB_FLAG_WHEEL_BLOCK)) return;
   const float *pp = c.pp[2];
   const float reach = c.blk_radius + sqrtf(c.rad * c.rad + c.hl * c.hl) + pp[7];
 #pragma unroll 1
@@ -980,7 +979,7 @@ BRB_D int env03_detect(const BrbModelConsts &c, const Phys &P, const Blk &B, flo
 // always go through coupled_solve_fast (with no chassis-block contact the coupling block is zero and the elimination
 // decouples exactly).  A single code path keeps the loop body inside the instruction cache: the first version had
 // separate robot / block / coupled solvers and was fetch-bound (ncu: stall_no_instruction 4.9 per issue, profiles/).
-template <int MAXIT>
+template <int MAXIT, bool WBON>
 BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&qstale)[4], float (&pstale)[3], Env03Stats &es, const unsigned wmask, const bool ctasync) {
   int sidx = 0, it = 0, nbb = 0, qprev_nc = -1;
   bool need_setup = true, done = false;   // warp-uniform loop + explicit reconvergence: see phys_run
@@ -1010,15 +1009,14 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
         if (Q.nc != qprev_nc) Q.bits = 0xFFFFFFFFu;
         if (Q.nc > 0) es.coupled++;
       }
-      wb_setup(c, P, B, W);
-      if (W.nw != wprev_nw) W.bits = 0xFFu;
-      if (W.nw > 0 && Q.nc == 0) es.coupled++;
-      wprev_nw = W.nw;
-      es.coupled_last = (unsigned)(Q.nc + W.nw);
-      es.wb_last = W.near ? 1u : 0u;
-#ifdef BRB_PROBE_WB      // kernel-tuning experiment: count narrow-phase calls in the block-contact statistic
-      if (W.near) es.blk_contact += 1000u;
-#endif
+      if (WBON) {
+        wb_setup(c, P, B, W);
+        if (W.nw != wprev_nw) W.bits = 0xFFu;
+        if (W.nw > 0 && Q.nc == 0) es.coupled++;
+        wprev_nw = W.nw;
+        es.wb_last = W.near ? 1u : 0u;
+      }
+      es.coupled_last = (unsigned)(Q.nc + (WBON ? W.nw : 0));
       es.blk_last = B.nc > 0 ? 1u : 0u;
       qprev_nc = Q.nc;
       was = P.valid; wasn = B.nc;
@@ -1039,8 +1037,8 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
 #endif
     if (ctasync) BRB_CTA_SYNC(); else __syncwarp(wmask);
     if (done) {
-    } else if (P.valid || B.nc > 0 || Q.nc > 0 || W.nw > 0) {
-      if (W.nw > 0) coupled_solve_wb(c, P, B, Q, W, ar, ab);
+    } else if (P.valid || B.nc > 0 || Q.nc > 0 || (WBON && W.nw > 0)) {
+      if (WBON && W.nw > 0) coupled_solve_wb(c, P, B, Q, W, ar, ab);
       else coupled_solve_fast(c, P, B, Q, W, ar, ab);
       es.csolves++;
       // rows within eps of their switching surface keep their state; when the undamped iteration starts to cycle the band
@@ -1048,7 +1046,7 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
       const float eps = it < 2 ? 2e-4f : (it == 2 ? 8e-4f : (it == 3 ? 3.2e-3f : (it == 4 ? 1.28e-2f : 5.12e-2f)));
       const unsigned nr = P.valid ? phys_active_set<true>(c, P, ar, P.bits, eps) : P.bits;
       const unsigned nbl = blk_active_set(c, B, ab, B.bits, eps), nq = cb_active_set(c, Q, ar, ab, Q.bits, eps);
-      const unsigned nwb = W.nw > 0 ? wb_active_set(c, W, ar, ab, W.bits, eps) : W.bits;
+      const unsigned nwb = (WBON && W.nw > 0) ? wb_active_set(c, W, ar, ab, W.bits, eps) : W.bits;
       conv = (nr == P.bits) && (nbl == B.bits) && (nq == Q.bits) && (nwb == W.bits);
       P.bits = nr; B.bits = nbl; Q.bits = nq; W.bits = nwb;
       if (!conv && ++it >= 7) {
@@ -1064,7 +1062,7 @@ BRB_D void phys03_run(const BrbModelConsts &c, Phys &P, Blk &B, int nsub, KF (&q
         if (P.valid) P.bits = phys_active_set<true>(c, P, ar, P.bits);
         B.bits = blk_active_set(c, B, ab, B.bits);
         Q.bits = cb_active_set(c, Q, ar, ab, Q.bits);
-        if (W.nw > 0) W.bits = wb_active_set(c, W, ar, ab, W.bits);
+        if (WBON && W.nw > 0) W.bits = wb_active_set(c, W, ar, ab, W.bits);
         conv = true;
       }
     } else {
@@ -1169,6 +1167,7 @@ BRB_D void reset_env03(const BrbState &S, long long i, const double *u, float o[
 }
 
 // One VecEnv.step of Env03-v2 for env i (Env03.step, env03_v1.py:26-58).  replay_u row = 8 re-fire slots + 32 reset slots.
+template <bool WBON>
 BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long long i, const float *__restrict__ actions,
                       float *__restrict__ obs, float *__restrict__ reward, uint8_t *__restrict__ done,
                       uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs, float *__restrict__ ep_return_out,
@@ -1215,7 +1214,7 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
   KF qprev[4];
   float pstale[3];
   Env03Stats es = {0u, 0u, 0u, 0u, 0u, 0u, 0u, 0u};
-  phys03_run<BRB_MAXIT>(c, st, B, c.frame_skip, qprev, pstale, es, wmask, ctasync);
+  phys03_run<BRB_MAXIT, WBON>(c, st, B, c.frame_skip, qprev, pstale, es, wmask, ctasync);
   stat[0] = c.frame_skip; stat[1] = st.n_contact; stat[2] = st.n_solve; stat[3] = st.n_nonconv; stat[7] = st.n_slots;
   stat[8] = es.coupled; stat[9] = es.blk_contact; stat[10] = es.fallback; stat[11] = es.csolves;
   {
@@ -1309,7 +1308,7 @@ BRB_D void step_env03(const BrbModelConsts &c, const BrbState &S, const long lon
       }
       near_wheel = near_wheel || !sep;
     }
-    if (c.flags & BRB_FLAG_WHEEL_BLOCK) near_wheel = false;     // the pair is generated (wb_setup): nothing unsupported about it
+    if (WBON) near_wheel = false;     // the pair is generated (wb_setup): nothing unsupported about it
 #ifdef BRB_PROBE_UNSUP   // kernel-tuning experiment: count one cause at a time (1 = chassis-floor, 2 = wheel flat, 4 = wheel near block)
     stat[4] = (((BRB_PROBE_UNSUP & 1) && low <= 0.0) || ((BRB_PROBE_UNSUP & 2) && tri <= 0.0) || ((BRB_PROBE_UNSUP & 4) && near_wheel)) ? 1u : 0u;
 #else

@@ -15,6 +15,9 @@
 #ifndef BRB_MINBLOCKS
 #define BRB_MINBLOCKS 3 // __launch_bounds__ min resident CTAs per SM (register cap = 65536 / (BRB_BLOCK * BRB_MINBLOCKS))
 #endif
+#define BRB_ENV03_V2_WB 4   // internal kernel instance: Env03-v2 with the opt-in wheel-block path compiled in (BRB_FLAG_WHEEL_BLOCK selects it at
+                            // launch, so the default instance carries none of it: 10.8 vs 11.4 ms per step with the path compiled in but off)
+#define BRB_IS_ENV03(KIND) ((KIND) == BRB_ENV03_V2 || (KIND) == BRB_ENV03_V2_WB)
 #define BRB_MAXIT 8     // cap on active-set (Newton) iterations per substep
 
 // Struct-of-arrays env state in HBM: column k of a [K][N] array lives at base + k*N, so a warp's 32

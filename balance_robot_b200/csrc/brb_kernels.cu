@@ -905,7 +905,7 @@ BRB_D void step_env(const BrbModelConsts &c, const BrbState &S, const long long 
 #ifdef BRB_MAXNREG   // kernel-tuning experiments: explicit register cap instead of the occupancy hint
 #define BRB_STEP_BOUNDS(KIND) __maxnreg__(BRB_MAXNREG)
 #else
-#define BRB_STEP_BOUNDS(KIND) __launch_bounds__((KIND == BRB_ENV03_V2) ? BRB_BLOCK_ENV03 : BRB_BLOCK, (KIND == BRB_ENV03_V2) ? BRB_MINBLOCKS_ENV03 : BRB_MINBLOCKS)
+#define BRB_STEP_BOUNDS(KIND) __launch_bounds__(BRB_IS_ENV03(KIND) ? BRB_BLOCK_ENV03 : BRB_BLOCK, BRB_IS_ENV03(KIND) ? BRB_MINBLOCKS_ENV03 : BRB_MINBLOCKS)
 #endif
 // One robot of the visit order per lane: step it, publish its group key for the next step's order, add to the statistics.
 template <int KIND>
@@ -921,7 +921,7 @@ __device__ __forceinline__ void step_batch(const BrbModelConsts &c, const BrbSta
   unsigned stat[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   const unsigned wmask = __ballot_sync(0xFFFFFFFFu, live);   // lanes of this warp that run a robot
   if (live) {
-    if (KIND == BRB_ENV03_V2) step_env03(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat, wmask, ctasync);
+    if (BRB_IS_ENV03(KIND)) step_env03<KIND == BRB_ENV03_V2_WB>(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat, wmask, ctasync);
     else step_env<KIND>(c, S, i, actions, obs, reward, done, truncated, terminal_obs, ep_return_out, ep_len_out, replay_u, stat, wmask);
   }
   if (perm.key_out) {
@@ -956,7 +956,7 @@ __device__ __forceinline__ void step_batch(const BrbModelConsts &c, const BrbSta
     if (a5) atomicAdd(&S.stats[BRB_STAT_EPISODES], a5);
     atomicAdd(&S.stats[BRB_STAT_ENV_STEPS], a6);
     atomicAdd(&S.stats[BRB_STAT_CONTACT_SLOTS], a7);
-    if (KIND == BRB_ENV03_V2) {
+    if (BRB_IS_ENV03(KIND)) {
       const unsigned long long a8 = stat8, a9 = stat9;
       if (a8) atomicAdd(&S.stats[BRB_STAT_COUPLED_SUBSTEPS], a8);
       if (a9) atomicAdd(&S.stats[BRB_STAT_BLOCK_CONTACT_SUBSTEPS], a9);
@@ -973,11 +973,11 @@ __global__ void BRB_STEP_BOUNDS(KIND) brb_step_kernel(const __grid_constant__ Br
                                                 uint8_t *__restrict__ truncated, float *__restrict__ terminal_obs,
                                                 float *__restrict__ ep_return_out, int32_t *__restrict__ ep_len_out,
                                                 const double *__restrict__ replay_u) {
-  for (int k = threadIdx.x; k < 16 * 5; k += blockDim.x) stab_fill(c, KIND == BRB_ENV03_V2, k);
+  for (int k = threadIdx.x; k < 16 * 5; k += blockDim.x) stab_fill(c, BRB_IS_ENV03(KIND), k);
   // Work queue (Env01-*): the launch has at most one resident wave of CTAs and every WARP pulls the next 32 robots of the visit
   // order from an atomic cursor until the order is exhausted.  A fixed one-robot-per-thread grid of 512 CTAs on 444 slots runs
   // 1.15 waves: the tail wave costs a whole step-time for 13 % of the robots.
-  const bool queue = KIND != BRB_ENV03_V2 && perm.cursor != nullptr;
+  const bool queue = !BRB_IS_ENV03(KIND) && perm.cursor != nullptr;
   long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   // Env03-v2: when every thread of the CTA runs a robot, its warps walk the substep loop in lockstep (CTA barriers at the
   // phase boundaries) so that they share the instruction cache: the loop body is 80 KB per trip, the L1.5 I-cache 32 KB
@@ -1187,7 +1187,10 @@ extern "C" void brb_launch_step(int kind, const BrbModelConsts *c, const BrbStat
       brb_step_kernel<BRB_ENV01_V3><<<grid, BRB_BLOCK, 0, stream>>>(*c, *S, *perm, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
       break;
     default:
-      brb_step_kernel<BRB_ENV03_V2><<<(unsigned)((S->n + BRB_BLOCK_ENV03 - 1) / BRB_BLOCK_ENV03), BRB_BLOCK_ENV03, 0, stream>>>(*c, *S, *perm, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
+      if (c->flags & BRB_FLAG_WHEEL_BLOCK)
+        brb_step_kernel<BRB_ENV03_V2_WB><<<(unsigned)((S->n + BRB_BLOCK_ENV03 - 1) / BRB_BLOCK_ENV03), BRB_BLOCK_ENV03, 0, stream>>>(*c, *S, *perm, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
+      else
+        brb_step_kernel<BRB_ENV03_V2><<<(unsigned)((S->n + BRB_BLOCK_ENV03 - 1) / BRB_BLOCK_ENV03), BRB_BLOCK_ENV03, 0, stream>>>(*c, *S, *perm, actions, obs, reward, done, truncated, terminal_obs, ep_return, ep_len, replay_u);
       break;
   }
 }

@@ -58,7 +58,10 @@ template <int KIND> static void step_all(Emu *e, const float *actions, float *ob
   for (int k = 0; k < 16 * 5; k++) stab_fill(e->c, KIND == BRB_ENV03_V2, k);     // the kernel's per-CTA shared-memory table
   for (long long i = 0; i < e->S.n; i++) {
     unsigned stat[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
-    if (KIND == BRB_ENV03_V2) step_env03(e->c, e->S, i, actions, obs, reward, done, trunc, tobs, epr, epl, replay, stat, 1u, false);
+    if (KIND == BRB_ENV03_V2) {
+      if (e->c.flags & BRB_FLAG_WHEEL_BLOCK) step_env03<true>(e->c, e->S, i, actions, obs, reward, done, trunc, tobs, epr, epl, replay, stat, 1u, false);
+      else step_env03<false>(e->c, e->S, i, actions, obs, reward, done, trunc, tobs, epr, epl, replay, stat, 1u, false);
+    }
     else step_env<KIND>(e->c, e->S, i, actions, obs, reward, done, trunc, tobs, epr, epl, replay, stat, 1u);
     for (int k = 0; k < 6; k++) e->stats[k] += stat[k];
     e->stats[BRB_STAT_CONTACT_SLOTS] += stat[7];
