@@ -449,14 +449,17 @@ int env03_coupled_solve(const BrbModelConsts &c, const Phys &P, const GContact *
 // the block, position from two alternating projections between the two support features.  Rare path: not inlined, loops not unrolled.
 #define CYLBOX_TAU 0.02f
 BRB_D float soft_signf(float x) { return fmaxf(-1.f, fminf(1.f, x / CYLBOX_TAU)); }
+// sqrt(max(x, 0)) as x * rsqrt(x): the IEEE sqrtf has an out-of-line slow path (32 CALLs in this function), and the collider runs on one
+// lane of a warp in cold code, where every instruction counts
+BRB_D float cb_sqrtf(float x) { const float y = fmaxf(x, 1e-30f); return y * rsqrtf(y); }
 BRB_D float cyl_box_sep(const float *d, const float *delta, const float *a, float R, float L, const float (*E)[3], float h) {
   const float da = dot3f(d, a);
-  return dot3f(d, delta) - L * fabsf(da) - R * sqrtf(fmaxf(0.f, 1.f - da * da)) - h * (fabsf(dot3f(d, E[0])) + fabsf(dot3f(d, E[1])) + fabsf(dot3f(d, E[2])));
+  return dot3f(d, delta) - L * fabsf(da) - R * cb_sqrtf(1.f - da * da) - h * (fabsf(dot3f(d, E[0])) + fabsf(dot3f(d, E[1])) + fabsf(dot3f(d, E[2])));
 }
 BRB_D void cyl_box_try(const float *v, bool orient, const float *delta, const float *a, float R, float L, const float (*E)[3], float h, float &best, float *bd) {
   const float n2 = dot3f(v, v);
   if (n2 <= 1e-16f) return;
-  float in = 1.f / sqrtf(n2);
+  float in = rsqrtf(n2);
   if (orient && dot3f(v, delta) < 0.f) in = -in;
   const float t[3] = {v[0] * in, v[1] * in, v[2] * in};
   const float sp = cyl_box_sep(t, delta, a, R, L, E, h);
@@ -470,21 +473,30 @@ BRB_D float cyl_box_cos16(int k) {      // cos(2 pi k / 16); sin = entry (k + 12
 }
 BRB_D float cyl_box_g(float c, float s, float D1, float D2, float A1, float A2, float R, float L, float h) {
   const float da = A1 * c + A2 * s;
-  return D1 * c + D2 * s - L * fabsf(da) - R * sqrtf(fmaxf(0.f, 1.f - da * da)) - h * (fabsf(c) + fabsf(s));
+  return D1 * c + D2 * s - L * fabsf(da) - R * cb_sqrtf(1.f - da * da) - h * (fabsf(c) + fabsf(s));
 }
+// arguments and result travel BY VALUE: through pointers the box axes were local-memory loads in every one of the ~100 separation
+// evaluations (145 us per call, one lane active; the first version of the opt-in path ran at 87 ms per step)
+struct CylBoxIn { float cc[3], a[3], b[3], E[3][3], R, L, h, margin; };
+struct CylBoxOut { int hit; float dist, n[3], pos[3]; };
 #ifdef BRB_HOST_EMU
 static
 #else
 __device__ __noinline__
 #endif
-int env03_cyl_box(const float *cc, const float *a, float R, float L, const float *b, const float (*E)[3], float h, float margin,
-                  float *dist_out, float *nrm, float *pos) {
+CylBoxOut env03_cyl_box(const CylBoxIn in_) {
+  const float cc[3] = {in_.cc[0], in_.cc[1], in_.cc[2]}, a[3] = {in_.a[0], in_.a[1], in_.a[2]}, b[3] = {in_.b[0], in_.b[1], in_.b[2]};
+  const float E[3][3] = {{in_.E[0][0], in_.E[0][1], in_.E[0][2]}, {in_.E[1][0], in_.E[1][1], in_.E[1][2]}, {in_.E[2][0], in_.E[2][1], in_.E[2][2]}};
+  const float R = in_.R, L = in_.L, h = in_.h, margin = in_.margin;
+  CylBoxOut out;
+  out.hit = 0; out.dist = 0.f;
+  for (int k = 0; k < 3; k++) { out.n[k] = 0.f; out.pos[k] = 0.f; }
   const float delta[3] = {b[0] - cc[0], b[1] - cc[1], b[2] - cc[2]};
   float best = -1e30f, bd[3] = {0.f, 0.f, 1.f};
-#pragma unroll 1
+#pragma unroll
   for (int i = 0; i < 3; i++) cyl_box_try(E[i], true, delta, a, R, L, E, h, best, bd);
   cyl_box_try(a, true, delta, a, R, L, E, h, best, bd);
-#pragma unroll 1
+#pragma unroll
   for (int i = 0; i < 3; i++) {
     const float x[3] = {a[1] * E[i][2] - a[2] * E[i][1], a[2] * E[i][0] - a[0] * E[i][2], a[0] * E[i][1] - a[1] * E[i][0]};
     if (dot3f(x, x) > 1e-10f) cyl_box_try(x, true, delta, a, R, L, E, h, best, bd);
@@ -497,9 +509,8 @@ int env03_cyl_box(const float *cc, const float *a, float R, float L, const float
     const float rho2 = dot3f(up, up);
     if (rho2 <= 1e-16f) continue;
     cyl_box_try(up, false, delta, a, R, L, E, h, best, bd);
-#pragma unroll 1
-    for (int cap = 0; cap < 2; cap++) {
-      const float sg = cap ? -1.f : 1.f, ir = R / sqrtf(rho2);
+    {   // ... and against the rim of the cap on the vertex's side of the wheel (the other rim is farther from it)
+      const float sg = ua < 0.f ? -1.f : 1.f, ir = R * rsqrtf(rho2);
       float t[3];
       for (int k = 0; k < 3; k++) t[k] = u[k] - sg * L * a[k] - up[k] * ir;
       cyl_box_try(t, false, delta, a, R, L, E, h, best, bd);
@@ -508,8 +519,8 @@ int env03_cyl_box(const float *cc, const float *a, float R, float L, const float
   // box edge against a rim / the curved side / a cap: the separating direction is perpendicular to the edge, d(phi) = cos(phi) E_a1 +
   // sin(phi) E_a2; sep restricted to that plane is a one-dimensional function (all four parallel edges and both caps at once), maximised
   // by a 16-point scan and a golden-section search with a fixed number of steps inside the best cell (no trigonometry per step)
-#pragma unroll 1
-  for (int ax = 0; ax < 3; ax++) {
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {      // unrolled: E[a1], E[a2] stay register-indexed
     const int a1 = (ax + 1) % 3, a2 = (ax + 2) % 3;
     const float D1 = dot3f(E[a1], delta), D2 = dot3f(E[a2], delta), A1 = dot3f(E[a1], a), A2 = dot3f(E[a2], a);
     int kb = 0;
@@ -523,30 +534,30 @@ int env03_cyl_box(const float *cc, const float *a, float R, float L, const float
     float lo = -tmax, hi = tmax, x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo), f1 = 0.f, f2 = 0.f;
     int fresh = 2;
 #pragma unroll 1
-    for (int it = 0; it < 14; it++) {
+    for (int it = 0; it < 10; it++) {
 #pragma unroll 1
       for (int w = 0; w < 2; w++) {
         if (fresh != 2 && w != fresh) continue;
-        const float t = w ? x2 : x1, in = 1.f / sqrtf(1.f + t * t);
+        const float t = w ? x2 : x1, in = rsqrtf(1.f + t * t);
         const float g = cyl_box_g((ck - t * sk) * in, (sk + t * ck) * in, D1, D2, A1, A2, R, L, h);
         if (w) f2 = g; else f1 = g;
       }
       if (f1 > f2) { hi = x2; x2 = x1; f2 = f1; x1 = hi - gr * (hi - lo); fresh = 0; }
       else { lo = x1; x1 = x2; f1 = f2; x2 = lo + gr * (hi - lo); fresh = 1; }
     }
-    const float t = 0.5f * (lo + hi), in = 1.f / sqrtf(1.f + t * t), cf = (ck - t * sk) * in, sf = (sk + t * ck) * in;
+    const float t = 0.5f * (lo + hi), in = rsqrtf(1.f + t * t), cf = (ck - t * sk) * in, sf = (sk + t * ck) * in;
     float td[3];
     for (int k = 0; k < 3; k++) td[k] = cf * E[a1][k] + sf * E[a2][k];
     cyl_box_try(td, false, delta, a, R, L, E, h, best, bd);
   }
-  if (best > margin) return 0;
+  if (best > margin) return out;
   // contact point: support features along bd refined by two alternating projections; feature selection blended over 0.02 rad around
   // perpendicular (see the oracle: continuous from the middle of a flat-on-flat patch to its deeper end)
   const float sa = soft_signf(dot3f(bd, a));
   float sb[3], rdir[3] = {0.f, 0.f, 0.f}, wr = 0.f;
   for (int j = 0; j < 3; j++) sb[j] = soft_signf(dot3f(bd, E[j]));
   {
-    const float da = dot3f(bd, a), dp[3] = {bd[0] - da * a[0], bd[1] - da * a[1], bd[2] - da * a[2]}, pm = sqrtf(dot3f(dp, dp));
+    const float da = dot3f(bd, a), dp[3] = {bd[0] - da * a[0], bd[1] - da * a[1], bd[2] - da * a[2]}, pm = cb_sqrtf(dot3f(dp, dp));
     if (pm > 1e-12f) { for (int k = 0; k < 3; k++) rdir[k] = dp[k] / pm; wr = fminf(1.f, pm / CYLBOX_TAU); }
   }
   float pc[3], qb[3];
@@ -563,12 +574,13 @@ int env03_cyl_box(const float *cc, const float *a, float R, float L, const float
     const float t = sa * L + (1.f - fabsf(sa)) * fmaxf(-L, fminf(L, ta));
     float rv[3];
     for (int k = 0; k < 3; k++) rv[k] = rl[k] - ta * a[k];
-    { const float n2 = dot3f(rv, rv); if (n2 > R * R) { const float in = R / sqrtf(n2); for (int k = 0; k < 3; k++) rv[k] *= in; } }
+    { const float n2 = dot3f(rv, rv); if (n2 > R * R) { const float in = R * rsqrtf(n2); for (int k = 0; k < 3; k++) rv[k] *= in; } }
     for (int k = 0; k < 3; k++) pc[k] = cc[k] + t * a[k] + wr * R * rdir[k] + (1.f - wr) * rv[k];
   }
-  *dist_out = best;
-  for (int k = 0; k < 3; k++) { nrm[k] = bd[k]; pos[k] = 0.5f * (pc[k] + qb[k]); }
-  return 1;
+  out.hit = 1;
+  out.dist = best;
+  for (int k = 0; k < 3; k++) { out.n[k] = bd[k]; out.pos[k] = 0.5f * (pc[k] + qb[k]); }
+  return out;
 }
 
 // Wheel-block contacts of the current substep: at most one per wheel, each with its own frame and the wheel's column of the point map
@@ -612,9 +624,14 @@ BRB_D void wb_setup(const BrbModelConsts &c, const Phys &P, const Blk &B, WBSet 
       if (sepd) continue;
     }
     W.near = true;
-    float dist, nn[3], pos[3];
-    if (!env03_cyl_box(cw, ax, c.rad, c.hl, B.p, Bx, c.blk_half, pp[7], &dist, nn, pos)) continue;
-    if (dist >= pp[7]) continue;
+    CylBoxIn ci;
+    for (int j = 0; j < 3; j++) { ci.cc[j] = cw[j]; ci.a[j] = ax[j]; ci.b[j] = B.p[j]; ci.E[0][j] = Bx[0][j]; ci.E[1][j] = Bx[1][j]; ci.E[2][j] = Bx[2][j]; }
+    ci.R = c.rad; ci.L = c.hl; ci.h = c.blk_half; ci.margin = pp[7];
+    const CylBoxOut co = env03_cyl_box(ci);
+    if (!co.hit || co.dist >= pp[7]) continue;
+    const float dist = co.dist;
+    float nn[3] = {co.n[0], co.n[1], co.n[2]};
+    const float pos[3] = {co.pos[0], co.pos[1], co.pos[2]};
     const int m = W.nw++;
     float t1[3], t2[3];
     make_frame3(nn, t1, t2);

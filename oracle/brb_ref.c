@@ -514,7 +514,7 @@ static void collide_box_box(const BrbRefModel *m, BrbRefData *d, int pair) {
  *   sep(d) = d.(c2 - c1) - h_cyl(d) - h_box(d)  is a lower bound of the signed distance for every unit d (support functions), and
  *   the signed distance is its maximum.  It is evaluated on the directions at which the maximum can sit for these two shapes:
  *   box face normals (3), the cylinder axis, axis x box edge (3: edge against the curved side), the radial direction to each box vertex
- *   (8: vertex against the curved side), the direction from the nearest rim point of either cap to each vertex (16), and for each box
+ *   (8: vertex against the curved side), the direction from the nearest rim point to each vertex (8), and for each box
  *   edge direction the best direction perpendicular to it (edge against a rim circle: a one-dimensional search, see below).  The contact point comes from two alternating projections between the
  *   support feature of the box and of the cylinder along the chosen direction. */
 static double cyl_box_sep(const double *dir, const double *delta, const double *a, double R, double L, const double E[3][3], const double *h) {
@@ -561,9 +561,9 @@ int brb_ref_cylinder_box(const double c[3], const double a_in[3], double R, doub
     if (rho2 <= 1e-16) continue;
     /* vertex against the curved side: radial direction (no re-orientation: it points from the axis to the vertex) */
     cyl_box_try(up, 0, delta, a, R, L, E, h, &best, bd);
-    /* vertex against the rim of either cap: from the nearest rim point to the vertex */
-    for (int cap = 0; cap < 2; cap++) {
-      double sg = cap ? -1.0 : 1.0, ir = R / sqrt(rho2), t[3];
+    /* vertex against the rim of the cap on its side of the cylinder (the other rim is farther): from the nearest rim point to the vertex */
+    {
+      double sg = ua < 0 ? -1.0 : 1.0, ir = R / sqrt(rho2), t[3];
       for (int k = 0; k < 3; k++) t[k] = u[k] - sg * L * a[k] - up[k] * ir;
       cyl_box_try(t, 0, delta, a, R, L, E, h, &best, bd);
     }
@@ -585,7 +585,7 @@ int brb_ref_cylinder_box(const double c[3], const double a_in[3], double R, doub
     const double ck = CYLBOX_COS16[kb], sk = CYLBOX_COS16[(kb + 12) & 15], tmax = 0.41421356237309503 /* tan(pi/8) */, gr = 0.6180339887498949;
     double lo = -tmax, hi = tmax, x1 = hi - gr * (hi - lo), x2 = lo + gr * (hi - lo), f1 = 0, f2 = 0;
     int fresh = 2;
-    for (int it = 0; it < 14; it++) {
+    for (int it = 0; it < 10; it++) {
       for (int w = 0; w < 2; w++) {
         if (fresh != 2 && w != fresh) continue;
         const double t = w ? x2 : x1, in = 1.0 / sqrt(1.0 + t * t);

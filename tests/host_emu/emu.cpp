@@ -108,6 +108,11 @@ extern "C" void emu_get_stats(Emu *e, unsigned long long *out) { memcpy(out, e->
 // test hook: the fp32 cylinder-box collider of brb_env03.cuh on its own (tests/test_env03_parity.py compares it with the oracle's)
 extern "C" int emu_cyl_box(const float *c, const float *a, float R, float L, const float *b, const float *E_rows, float h, float margin,
                            float *dist, float *nrm, float *pos) {
-  const float E[3][3] = {{E_rows[0], E_rows[1], E_rows[2]}, {E_rows[3], E_rows[4], E_rows[5]}, {E_rows[6], E_rows[7], E_rows[8]}};
-  return env03_cyl_box(c, a, R, L, b, E, h, margin, dist, nrm, pos);
+  CylBoxIn ci;
+  for (int j = 0; j < 3; j++) { ci.cc[j] = c[j]; ci.a[j] = a[j]; ci.b[j] = b[j]; ci.E[0][j] = E_rows[j]; ci.E[1][j] = E_rows[3 + j]; ci.E[2][j] = E_rows[6 + j]; }
+  ci.R = R; ci.L = L; ci.h = h; ci.margin = margin;
+  const CylBoxOut co = env03_cyl_box(ci);
+  *dist = co.dist;
+  for (int j = 0; j < 3; j++) { nrm[j] = co.n[j]; pos[j] = co.pos[j]; }
+  return co.hit;
 }
