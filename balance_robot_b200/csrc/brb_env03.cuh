@@ -654,10 +654,6 @@ BRB_D void wb_setup(const BrbModelConsts &c, const Phys &P, const Blk &B, WBSet 
     W.y[m][0] = pp[2] * dot3f(nn, dv) + pp[1] * imp * (dist - pp[7]);
     W.y[m][1] = pp[2] * dot3f(t1, dv);
     W.y[m][2] = pp[2] * dot3f(t2, dv);
-#if defined(BRB_HOST_EMU) && defined(BRB_EMU_DEBUG)
-    printf("[wb] wheel %d dist %.6e n %.5f %.5f %.5f pos %.6f %.6f %.6f ra %.5f %.5f %.5f wv %.5f %.5f %.5f y %.4e %.4e %.4e D %.4e\n", k, dist, nn[0], nn[1], nn[2],
-           pos[0], pos[1], pos[2], ra[0], ra[1], ra[2], wv[0], wv[1], wv[2], W.y[m][0], W.y[m][1], W.y[m][2], W.D[m]);
-#endif
   }
 }
 
