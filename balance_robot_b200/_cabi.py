@@ -16,7 +16,7 @@ CSRC = pathlib.Path(__file__).resolve().parent / "csrc"
 LIB_PATH = CSRC / "libbrb_cuda.so"
 _EXPERIMENT_LIB = "BRB_EXPERIMENT_LIB"   # kernel-tuning experiments only (scripts/): alternative build of the SAME sources
 SOURCES = ("brb_kernels.cu", "brb_cabi.cu", "brb_policy.cu", "brb_policy_tc.cu")
-HEADERS = (CSRC / "brb_internal.h", CSRC / "brb_policy_layout.h", CSRC / "brb_chol8.inc", CSRC / "brb_chol8z.inc", CSRC / "brb_chol6.inc", CSRC / "brb_schur6.inc", CSRC / "brb_env03.cuh",
+HEADERS = (CSRC / "brb_internal.h", CSRC / "brb_policy_layout.h", CSRC / "brb_chol8.inc", CSRC / "brb_chol8z.inc", CSRC / "brb_chol6.inc", CSRC / "brb_schur6.inc", CSRC / "brb_schur6w.inc", CSRC / "brb_env03.cuh",
            CSRC.parent.parent / "include" / "brb.h")
 # -ftz=true: no denormal handling around MUFU.RSQ / RCP (the state is O(1); 0.895 -> 0.859 ms per step at 65,536 robots)
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-ftz=true",
