@@ -516,6 +516,7 @@ CylBoxOut env03_cyl_box(const CylBoxIn in_) {
       cyl_box_try(t, false, delta, a, R, L, E, h, best, bd);
     }
   }
+  if (best > margin) return out;     // already separated by more than the margin along one of the cheap directions: the maximum only grows
   // box edge against a rim / the curved side / a cap: the separating direction is perpendicular to the edge, d(phi) = cos(phi) E_a1 +
   // sin(phi) E_a2; sep restricted to that plane is a one-dimensional function (all four parallel edges and both caps at once), maximised
   // by a 16-point scan and a golden-section search with a fixed number of steps inside the best cell (no trigonometry per step)
